@@ -1,0 +1,435 @@
+"""CPU oracle: plain PyTorch fp32 restatement of the Helping-Hands video-side forward path.
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package.  It exists so that the
+CUDA path can be checked on the GPU box, where /root/reference is absent.
+
+Parity status: PINNED.  `oracle/make_golden.py` runs the unmodified reference (imported through
+`oracle/ref_import.py`) and this restatement on identical seeded state_dicts / inputs and commits
+the reference outputs under tests/golden/; `tests/test_oracle_golden.py` re-checks the restatement
+against those fixtures everywhere and against the live reference when /root/reference exists.
+
+Everything here is a function of (state_dict, inputs); state_dict keys are exactly the reference's
+(SURVEY.md §8b).  Citations are to files under /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------
+# deterministic synthetic weights (shared by tests, smoke and bench; no reference code involved)
+# --------------------------------------------------------------------------------------------
+
+def encoder_param_shapes(D, L, patch, n, T, hidden=None):
+    hidden = hidden or 4 * D
+    s = {"cls_token": (1, 1, D), "pos_embed": (1, n + 1, D), "temporal_embed": (1, T, D),
+         "patch_embed.proj.weight": (D, 3, patch, patch),
+         "ln_pre.weight": (D,), "ln_pre.bias": (D,), "norm.weight": (D,), "norm.bias": (D,)}
+    for i in range(L):
+        p = "blocks.%d." % i
+        for nm in ("norm1", "norm2", "norm3"):
+            s[p + nm + ".weight"] = (D,)
+            s[p + nm + ".bias"] = (D,)
+        for at in ("attn", "timeattn"):
+            s[p + at + ".qkv.weight"] = (3 * D, D)
+            s[p + at + ".qkv.bias"] = (3 * D,)
+            s[p + at + ".proj.weight"] = (D, D)
+            s[p + at + ".proj.bias"] = (D,)
+        s[p + "mlp.fc1.weight"] = (hidden, D)
+        s[p + "mlp.fc1.bias"] = (hidden,)
+        s[p + "mlp.fc2.weight"] = (D, hidden)
+        s[p + "mlp.fc2.bias"] = (D,)
+    return s
+
+
+def decoder_param_shapes(C, Q, n, T, F_in, ncls1, layers=6, ffn=2048, pred_traj=True, text_width=768):
+    s = {"pos_embed": (1, n + 1, C), "temporal_embed": (1, T, C),
+         "txt_proj.1.weight": (256, text_width), "txt_proj.1.bias": (256,),
+         "vid_proj.0.weight": (256, text_width), "vid_proj.0.bias": (256,),
+         "transformer.pre_norm.weight": (C,), "transformer.pre_norm.bias": (C,),
+         "transformer.decoder.norm.weight": (C,), "transformer.decoder.norm.bias": (C,),
+         "class_embed.weight": (ncls1, C), "class_embed.bias": (ncls1,),
+         "query_embed.weight": (Q, C), "proj.weight": (C, F_in),
+         "obj_proj.0.weight": (C, C), "obj_proj.0.bias": (C,),
+         "obj_proj.2.weight": (256, C), "obj_proj.2.bias": (256,)}
+    dims = [C, C, C, 4]
+    for j in range(3):
+        s["bbox_embed.layers.%d.weight" % j] = (dims[j + 1], dims[j])
+        s["bbox_embed.layers.%d.bias" % j] = (dims[j + 1],)
+    if pred_traj:
+        s["frame_index.weight"] = (T, C)
+        s["frame_proj.weight"] = (C, 2 * C)
+        s["frame_proj.bias"] = (C,)
+    for i in range(layers):
+        p = "transformer.decoder.layers.%d." % i
+        for at in ("multihead_attn", "self_attn"):
+            s[p + at + ".in_proj_weight"] = (3 * C, C)
+            s[p + at + ".in_proj_bias"] = (3 * C,)
+            s[p + at + ".out_proj.weight"] = (C, C)
+            s[p + at + ".out_proj.bias"] = (C,)
+        s[p + "linear1.weight"] = (ffn, C)
+        s[p + "linear1.bias"] = (ffn,)
+        s[p + "linear2.weight"] = (C, ffn)
+        s[p + "linear2.bias"] = (C,)
+        for nm in ("norm1", "norm2", "norm3"):
+            s[p + nm + ".weight"] = (C,)
+            s[p + nm + ".bias"] = (C,)
+    return s
+
+
+def clip_param_shapes(D, L, patch, n, T, text_width=768, text_layers=12, embed_dim=256, vocab=49408, ctx=77):
+    """Full backbone state_dict: visual.* + text tower + projections (SURVEY.md §8b key list)."""
+    s = {"visual." + k: v for k, v in encoder_param_shapes(D, L, patch, n, T).items()}
+    W = text_width
+    s.update({"positional_embedding": (ctx, W), "image_projection": (D, embed_dim), "text_projection": (W, embed_dim),
+              "logit_scale": (), "token_embedding.weight": (vocab, W), "ln_final.weight": (W,), "ln_final.bias": (W,)})
+    for i in range(text_layers):
+        p = "transformer.resblocks.%d." % i
+        s[p + "attn.in_proj_weight"] = (3 * W, W)
+        s[p + "attn.in_proj_bias"] = (3 * W,)
+        s[p + "attn.out_proj.weight"] = (W, W)
+        s[p + "attn.out_proj.bias"] = (W,)
+        for nm in ("ln_1", "ln_2"):
+            s[p + nm + ".weight"] = (W,)
+            s[p + nm + ".bias"] = (W,)
+        s[p + "mlp.c_fc.weight"] = (4 * W, W)
+        s[p + "mlp.c_fc.bias"] = (4 * W,)
+        s[p + "mlp.c_proj.weight"] = (W, 4 * W)
+        s[p + "mlp.c_proj.bias"] = (W,)
+    return s
+
+
+def synth_state_dict(shapes: Dict[str, tuple], seed: int) -> Dict[str, Tensor]:
+    """Seeded synthetic weights.  Every tensor is re-randomised (the reference's `time_init='zeros'`
+    would otherwise leave the temporal attention a no-op): matrices ~ N(0, fan_in^-1/2
+    scaled), LayerNorm weights ~ 1 + 0.1 N(0,1), biases / embeddings ~ 0.02-0.1 N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = shapes[k]
+        r = torch.randn(shp, generator=g, dtype=torch.float32)
+        leaf = k.split(".")[-1]
+        is_norm = ("norm" in k or "ln_" in k) and len(shp) == 1
+        if is_norm and leaf == "weight":
+            t = 1.0 + 0.1 * r
+        elif is_norm:
+            t = 0.05 * r
+        elif len(shp) == 1:
+            t = 0.05 * r
+        elif k in ("query_embed.weight", "frame_index.weight"):
+            t = 0.5 * r
+        elif leaf in ("pos_embed", "temporal_embed", "cls_token", "positional_embedding") or k == "token_embedding.weight":
+            t = 0.1 * r
+        elif k == "logit_scale":
+            t = torch.tensor(math.log(1 / 0.07))
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            t = r * (0.8 / math.sqrt(fan_in))
+        sd[k] = t
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+# encoder  (model/LaviLa.py)
+# --------------------------------------------------------------------------------------------
+
+def quick_gelu(x: Tensor) -> Tensor:
+    """model/openai_model.py:177-179."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def _group_mask(T: int, n: int, mode: str) -> Tensor:
+    """Boolean [N,N] attention mask equivalent to VarAttention's splice/rearrange/cat
+    (model/LaviLa.py:255-276): query CLS sees every key; a patch query (f,p) sees the CLS key and
+    the keys of its group -- same p over frames for 'time', same f over patches for 'space'."""
+    N = 1 + T * n
+    idx = torch.arange(T * n)
+    f, p = idx // n, idx % n
+    grp = p if mode == "time" else f
+    m = torch.zeros(N, N, dtype=torch.bool)
+    m[0, :] = True
+    m[:, 0] = True
+    m[1:, 1:] = grp[:, None] == grp[None, :]
+    return m
+
+
+def var_attention(z: Tensor, w_qkv, b_qkv, w_proj, b_proj, heads: int, T: int, n: int, mode: str) -> Tensor:
+    """VarAttention.forward (model/LaviLa.py:246-283) as masked dense attention."""
+    B, N, D = z.shape
+    hd = D // heads
+    qkv = F.linear(z, w_qkv, b_qkv).view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * (hd ** -0.5), qkv[1], qkv[2]                      # :249-252
+    s = q @ k.transpose(-1, -2)
+    s = s.masked_fill(~_group_mask(T, n, mode).to(s.device), float("-inf"))
+    o = torch.softmax(s, dim=-1) @ v                                       # :194-198
+    o = o.permute(0, 2, 1, 3).reshape(B, N, D)
+    return F.linear(o, w_proj, b_proj)                                     # :281
+
+
+def encoder_block(x: Tensor, sd, pfx: str, heads: int, T: int, n: int, eps: float = 1e-6) -> Tensor:
+    """SpaceTimeBlock.forward, 'frozen-in-time' wiring (model/LaviLa.py:345-390)."""
+    D = x.shape[-1]
+    g = lambda k: sd[pfx + k]
+    ln = lambda t, nm: F.layer_norm(t, (D,), g(nm + ".weight"), g(nm + ".bias"), eps)
+    t_out = var_attention(ln(x, "norm3"), g("timeattn.qkv.weight"), g("timeattn.qkv.bias"),
+                          g("timeattn.proj.weight"), g("timeattn.proj.bias"), heads, T, n, "time")   # :353
+    tr = x + t_out                                                                                    # :364
+    s_out = var_attention(ln(tr, "norm1"), g("attn.qkv.weight"), g("attn.qkv.bias"),
+                          g("attn.proj.weight"), g("attn.proj.bias"), heads, T, n, "space")          # :372
+    sr = x + s_out                                                                                    # :384 (x, not tr)
+    h = quick_gelu(F.linear(ln(sr, "norm2"), g("mlp.fc1.weight"), g("mlp.fc1.bias")))                 # :186-187
+    return sr + F.linear(h, g("mlp.fc2.weight"), g("mlp.fc2.bias"))                                   # :388
+
+
+def encoder_embed(video: Tensor, sd, pfx: str = "") -> Tensor:
+    """Patch embed + CLS + pos/temporal embed + ln_pre (model/LaviLa.py:218-223,540-559)."""
+    B, T, C, H, W = video.shape
+    w = sd[pfx + "patch_embed.proj.weight"]
+    D, _, p, _ = w.shape
+    tok = F.conv2d(video.reshape(B * T, C, H, W), w, None, stride=p)         # no bias: ln_pre=True (:216)
+    n = tok.shape[-1] * tok.shape[-2]
+    tok = tok.flatten(2).transpose(1, 2).reshape(B, T * n, D)
+    pos = sd[pfx + "pos_embed"]
+    tpos = pos[:, 1:].repeat(1, T, 1) + sd[pfx + "temporal_embed"].repeat_interleave(n, 1)
+    x = torch.cat([sd[pfx + "cls_token"].expand(B, -1, -1) + pos[:, :1], tok + tpos], 1)
+    return F.layer_norm(x, (D,), sd[pfx + "ln_pre.weight"], sd[pfx + "ln_pre.bias"], 1e-5)            # :456 default eps
+
+
+def encoder_forward(video: Tensor, sd, heads: int, pfx: str = "", depth: Optional[int] = None,
+                    return_blocks: bool = False):
+    """SpaceTimeTransformer.forward_features (model/LaviLa.py:537-573) -> (x_cls [B,D], fmap [B,N,D])."""
+    B, T = video.shape[:2]
+    x = encoder_embed(video, sd, pfx)
+    D = x.shape[-1]
+    n = (x.shape[1] - 1) // T
+    if depth is None:
+        depth = 1 + max(int(k[len(pfx):].split(".")[1]) for k in sd if k.startswith(pfx + "blocks."))
+    blocks = []
+    for i in range(depth):
+        x = encoder_block(x, sd, "%sblocks.%d." % (pfx, i), heads, T, n)
+        if return_blocks:
+            blocks.append(x)
+    fmap = F.layer_norm(x, (D,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-6)               # :570,573
+    if return_blocks:
+        return fmap[:, 0], fmap, blocks
+    return fmap[:, 0], fmap
+
+
+def text_forward(tokens: Tensor, sd, heads: int) -> Tuple[Tensor, Tensor]:
+    """CLIP.encode_text (model/LaviLa.py:660-670) + ResidualAttentionBlock (model/openai_model.py:182-216)."""
+    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
+    G, Lc, W = x.shape
+    hd = W // heads
+    causal = torch.full((Lc, Lc), float("-inf")).triu_(1)
+    i = 0
+    while ("transformer.resblocks.%d.ln_1.weight" % i) in sd:
+        p = "transformer.resblocks.%d." % i
+        y = F.layer_norm(x, (W,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        qkv = F.linear(y, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"])
+        qkv = qkv.view(G, Lc, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        s = (qkv[0] * hd ** -0.5) @ qkv[1].transpose(-1, -2) + causal
+        o = (torch.softmax(s, -1) @ qkv[2]).permute(0, 2, 1, 3).reshape(G, Lc, W)
+        x = x + F.linear(o, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
+        y = F.layer_norm(x, (W,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        x = x + F.linear(quick_gelu(F.linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])),
+                         sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+        i += 1
+    x = F.layer_norm(x, (W,), sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    x_cls = x[torch.arange(G), tokens.argmax(-1)] @ sd["text_projection"]
+    return x_cls, x
+
+
+def clip_forward(video: Tensor, tokens: Optional[Tensor], sd, heads: int, text_heads: int = 12,
+                 norm_embed: bool = True) -> Dict[str, Tensor]:
+    """CLIP.forward(..., return_feature_map=True) (model/LaviLa.py:672-687)."""
+    x_cls, fmap = encoder_forward(video, sd, heads, pfx="visual.")
+    img = x_cls @ sd["image_projection"]                                                              # :657
+    out = {"image_feature_map": fmap}
+    if tokens is not None:
+        txt, tmap = text_forward(tokens, sd, text_heads)
+        out["text_feature_map"] = tmap
+    else:
+        txt = None
+    if norm_embed:
+        img = F.normalize(img, dim=-1)
+        txt = F.normalize(txt, dim=-1) if txt is not None else None
+    out["image_embed"] = img
+    if txt is not None:
+        out["text_embed"] = txt
+    if "logit_scale" in sd:
+        out["logit_scale"] = sd["logit_scale"].exp()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# object-aware decoder  (model/tfm_decoder.py)
+# --------------------------------------------------------------------------------------------
+
+def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, w, b, wo, bo, heads: int) -> Tensor:
+    """nn.MultiheadAttention forward (batch-first here), eval mode, no masks
+    (call sites model/tfm_decoder.py:433-441)."""
+    C = q_in.shape[-1]
+    hd = C // heads
+    q = F.linear(q_in, w[:C], b[:C])
+    k = F.linear(k_in, w[C:2 * C], b[C:2 * C])
+    v = F.linear(v_in, w[2 * C:], b[2 * C:])
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    q = q.view(B, Lq, heads, hd).transpose(1, 2) * (hd ** -0.5)
+    k = k.view(B, Lk, heads, hd).transpose(1, 2)
+    v = v.view(B, Lk, heads, hd).transpose(1, 2)
+    o = torch.softmax(q @ k.transpose(-1, -2), -1) @ v
+    return F.linear(o.transpose(1, 2).reshape(B, Lq, C), wo, bo)
+
+
+def decoder_pos_embed(sd, T: int) -> Tensor:
+    """ObjDecoder.construct_3d_pos_embed (model/tfm_decoder.py:161-166) -> [T*n, C]."""
+    pe = sd["pos_embed"][0, 1:]
+    te = sd["temporal_embed"][0]
+    n = pe.shape[0]
+    assert te.shape[0] == T, "reference requires T == num_frames (:161-166)"
+    return (pe[None, :, :] + te[:, None, :]).reshape(T * n, -1)
+
+
+def decoder_forward(features: Tensor, sd, heads: int = 8, pred_traj: bool = True,
+                    num_frames: Optional[int] = None):
+    """ObjDecoder.forward (model/tfm_decoder.py:183-233) with Cross_Attention.forward (:76-93),
+    TransformerDecoder.forward (:255-295) and TransformerDecoderLayer.forward_pre (:420-461, sa_first).
+    features [B,T,n,F] -> (out, hs[L,B,Q,C], [], [])."""
+    B, T, n, _ = features.shape
+    C = sd["proj.weight"].shape[0]
+    mem = F.linear(features, sd["proj.weight"]).reshape(B, T * n, C)                                  # :200
+    mem = F.layer_norm(mem, (C,), sd["transformer.pre_norm.weight"], sd["transformer.pre_norm.bias"], 1e-5)  # :86
+    pos = decoder_pos_embed(sd, T)
+    qpos = sd["query_embed.weight"][None].expand(B, -1, -1)
+    tgt = torch.zeros_like(qpos)                                                                      # :84
+    lnf = lambda t, p: F.layer_norm(t, (C,), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+    hs = []
+    L = 0
+    while ("transformer.decoder.layers.%d.norm1.weight" % L) in sd:
+        L += 1
+    for i in range(L):
+        p = "transformer.decoder.layers.%d." % i
+        t2 = lnf(tgt, p + "norm1")
+        tgt = tgt + _mha(t2 + qpos, t2 + qpos, t2, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                         sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], heads)
+        t2 = lnf(tgt, p + "norm2")
+        tgt = tgt + _mha(t2 + qpos, mem + pos, mem, sd[p + "multihead_attn.in_proj_weight"],
+                         sd[p + "multihead_attn.in_proj_bias"], sd[p + "multihead_attn.out_proj.weight"],
+                         sd[p + "multihead_attn.out_proj.bias"], heads)
+        t2 = lnf(tgt, p + "norm3")
+        tgt = tgt + F.linear(F.relu(F.linear(t2, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                             sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+        hs.append(lnf(tgt, "transformer.decoder.norm"))                                               # :282
+    hs = torch.stack(hs)                                                                              # [L,B,Q,C]
+    logits = F.linear(hs, sd["class_embed.weight"], sd["class_embed.bias"])                           # :208
+    nf = num_frames if num_frames is not None else sd["temporal_embed"].shape[1]
+    if pred_traj and T == nf:
+        Q = hs.shape[2]
+        wf = sd["frame_proj.weight"]
+        cond = F.linear(hs, wf[:, :C])[:, :, None] + \
+            (F.linear(sd["frame_index.weight"], wf[:, C:], sd["frame_proj.bias"]))[None, None, :, None, :]
+        cond = cond.reshape(L, B * T, Q, C)                                                           # :212-215
+        logits = logits[:, :, None].expand(-1, -1, 4, -1, -1).flatten(1, 2)                           # :216 literal 4
+    else:
+        cond = hs
+    x = cond
+    for j in range(3):
+        x = F.linear(x, sd["bbox_embed.layers.%d.weight" % j], sd["bbox_embed.layers.%d.bias" % j])
+        if j < 2:
+            x = F.relu(x)
+    boxes = x.sigmoid()                                                                               # :228
+    out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1],
+           "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]}
+    return out, hs, [], []
+
+
+def obj_proj(hs_last: Tensor, sd) -> Tensor:
+    """ObjDecoder.obj_proj (model/tfm_decoder.py:175-180)."""
+    return F.linear(F.relu(F.linear(hs_last, sd["obj_proj.0.weight"], sd["obj_proj.0.bias"])),
+                    sd["obj_proj.2.weight"], sd["obj_proj.2.bias"])
+
+
+def txt_proj(text_feat: Tensor, sd) -> Tensor:
+    """ObjDecoder.txt_proj = ReLU -> Linear(768,256) (model/tfm_decoder.py:170-171)."""
+    return F.linear(F.relu(text_feat), sd["txt_proj.1.weight"], sd["txt_proj.1.bias"])
+
+
+# --------------------------------------------------------------------------------------------
+# scoring and boxes  (model/metric.py, utils/box_ops.py, model/box_utils.py)
+# --------------------------------------------------------------------------------------------
+
+def sim_matrix(a: Tensor, b: Tensor, eps: float = 1e-8) -> Tensor:
+    """model/metric.py:363-375."""
+    a = a / a.norm(dim=-1, keepdim=True).clamp_min(eps)
+    b = b / b.norm(dim=-1, keepdim=True).clamp_min(eps)
+    return a @ b.transpose(-1, -2)
+
+
+def egomcq_choices(sims: Tensor) -> Tensor:
+    """argmax per question (model/metric.py:218): sims [G,1,5] or [G,5] -> int64 [G]."""
+    return sims.reshape(sims.shape[0], -1).argmax(-1)
+
+
+def egomcq_accuracy(preds: Tensor, labels: Tensor, types: Tensor) -> Dict[str, float]:
+    """model/metric.py:209-225: accuracy per question type (sorted unique), first = Intra, second = Inter."""
+    out = {}
+    for t, name in zip(torch.unique(types).tolist(), ["Intra-video", "Inter-video"]):
+        sel = types.reshape(-1) == t
+        ch = egomcq_choices(preds[sel])
+        out[name] = 100.0 * (ch == labels.reshape(-1)[sel]).float().mean().item()
+    return out
+
+
+def box_cxcywh_to_xyxy(x: Tensor) -> Tensor:
+    """utils/box_ops.py:9-13."""
+    cx, cy, w, h = x[..., 0], x[..., 1], x[..., 2], x[..., 3]
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+
+def box_xyxy_to_cxcywh(x: Tensor) -> Tensor:
+    """utils/box_ops.py:16-20."""
+    x0, y0, x1, y1 = x[..., 0], x[..., 1], x[..., 2], x[..., 3]
+    return torch.stack([(x0 + x1) / 2, (y0 + y1) / 2, x1 - x0, y1 - y0], -1)
+
+
+def box_iou(b1: Tensor, b2: Tensor) -> Tuple[Tensor, Tensor]:
+    """utils/box_ops.py:24-37 -- note the +1e-4 on the union (:36)."""
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = torch.maximum(b1[:, None, :2], b2[None, :, :2])
+    rb = torch.minimum(b1[:, None, 2:], b2[None, :, 2:])
+    wh = (rb - lt).clamp_min(0)
+    inter = wh[..., 0] * wh[..., 1]
+    union = a1[:, None] + a2[None, :] - inter
+    return inter / (union + 0.0001), union
+
+
+def generalized_box_iou(b1: Tensor, b2: Tensor) -> Tensor:
+    """utils/box_ops.py:40-61 (xyxy in, [N,M] out)."""
+    iou, union = box_iou(b1, b2)
+    lt = torch.minimum(b1[:, None, :2], b2[None, :, :2])
+    rb = torch.maximum(b1[:, None, 2:], b2[None, :, 2:])
+    wh = (rb - lt).clamp_min(0)
+    hull = wh[..., 0] * wh[..., 1]
+    return iou - (hull - union) / hull
+
+
+def matcher_cost(pred_cxcywh: Tensor, tgt_cxcywh: Tensor, w_bbox: float = 5.0, w_giou: float = 2.0) -> Tensor:
+    """HungarianMatcher cost with exclude_class=True (model/box_utils.py:75-88, weights :96)."""
+    l1 = torch.cdist(pred_cxcywh, tgt_cxcywh, p=1)
+    g = generalized_box_iou(box_cxcywh_to_xyxy(pred_cxcywh), box_cxcywh_to_xyxy(tgt_cxcywh))
+    return w_bbox * l1 + w_giou * (-g)
+
+
+def egonce_logprobs(sim: Tensor, temperature: float = 0.07) -> Tuple[Tensor, Tensor]:
+    """The softmax part of EgoNCE.forward (model/loss.py:61-69): log-softmax over rows and columns."""
+    return F.log_softmax(sim / temperature, dim=1), F.log_softmax(sim.t() / temperature, dim=1)

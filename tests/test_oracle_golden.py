@@ -1,0 +1,55 @@
+"""The oracle (oracle/hh_oracle.py) against the reference's outputs.
+
+* everywhere: against the committed fixtures in tests/golden/ (made by oracle/make_golden.py from the
+  unmodified reference);
+* in the build container (where /root/reference exists): against the live reference as well.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import golden_cases as gc
+from oracle import ref_import
+
+TOL = 1e-5   # fp32 CPU vs fp32 CPU, different op order (masked dense attention vs rearrange/cat)
+
+
+def _compare(ref, mine, name):
+    for k, v in ref.items():
+        if isinstance(v, torch.Tensor):
+            assert mine[k].shape == v.shape, (name, k)
+            err = (mine[k] - v).abs().max().item()
+            assert err <= TOL * max(1.0, v.abs().max().item()), (name, k, err)
+        else:
+            for kk in v:
+                assert abs(v[kk] - mine[k][kk]) < 1e-4, (name, k, kk)
+
+
+@pytest.mark.parametrize("name", sorted(gc.CASES))
+def test_oracle_matches_golden_fixture(name):
+    path = os.path.join(gc.GOLDEN_DIR, name + ".pt")
+    ref = torch.load(path)
+    _compare(ref, gc.run_oracle(gc.CASES[name]), name)
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("name", ["enc_tiny", "dec_tiny_traj", "dec_tiny_notraj", "boxes", "score"])
+def test_fixture_is_what_the_live_reference_says(name):
+    from oracle import make_golden
+    live = make_golden.run_reference(gc.CASES[name])
+    ref = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
+    for k, v in ref.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.allclose(live[k], v, atol=1e-6, rtol=1e-6), (name, k)
+
+
+def test_group_mask_semantics():
+    """CLS sees all, patches see CLS + own group (model/LaviLa.py:255-270)."""
+    from oracle import hh_oracle as O
+    m = O._group_mask(T=3, n=4, mode="time")
+    assert m[0].all() and m[:, 0].all()
+    # token (f=1,p=2) -> index 1+1*4+2 = 7 ; same p across frames: 3, 7, 11
+    assert m[7].nonzero().flatten().tolist() == [0, 3, 7, 11]
+    s = O._group_mask(T=3, n=4, mode="space")
+    assert s[7].nonzero().flatten().tolist() == [0, 5, 6, 7, 8]
