@@ -1,0 +1,248 @@
+// extern "C" surface declared in include/hh_b200.h.  No C++ types or exceptions cross this boundary.
+#include <dlfcn.h>
+
+#include <cstring>
+
+#include <new>
+
+#include "engine.h"
+
+using namespace hh;
+
+struct hh_encoder {
+  Encoder impl;
+  explicit hh_encoder(const hh_encoder_cfg& c) : impl(c) {}
+};
+struct hh_decoder {
+  Decoder impl;
+  explicit hh_decoder(const hh_decoder_cfg& c) : impl(c) {}
+};
+
+#define HH_GUARD_BEGIN try {
+#define HH_GUARD_END                                              \
+  }                                                               \
+  catch (const std::bad_alloc&) { return fail(-3, "host out of memory"); } \
+  catch (const std::exception& e) { return fail(-3, std::string("internal error: ") + e.what()); } \
+  catch (...) { return fail(-3, "internal error"); }
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* hh_last_error(void) { return last_error_cstr(); }
+int hh_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------ encoder
+int hh_encoder_create(hh_encoder** out, const hh_encoder_cfg* cfg) {
+  HH_GUARD_BEGIN
+  if (!out || !cfg) return fail(-2, "hh_encoder_create: null argument");
+  int rc = Encoder::validate(*cfg);
+  if (rc) return rc;
+  *out = new hh_encoder(*cfg);
+  return 0;
+  HH_GUARD_END
+}
+void hh_encoder_destroy(hh_encoder* enc) { delete enc; }
+int hh_encoder_set_weight(hh_encoder* enc, const char* key, const float* data, int64_t numel, void* stream) {
+  HH_GUARD_BEGIN
+  if (!enc) return fail(-1, "hh_encoder_set_weight: null handle");
+  if (!key || !data) return fail(-2, "hh_encoder_set_weight: null argument");
+  return enc->impl.weights.set(key, data, numel, S(stream));
+  HH_GUARD_END
+}
+int hh_encoder_forward_n(hh_encoder* enc, const float* video, int B, int nblocks, float* fmap, void* stream) {
+  HH_GUARD_BEGIN
+  if (!enc) return fail(-1, "hh_encoder_forward: null handle");
+  return enc->impl.forward(video, B, nblocks, fmap, S(stream));
+  HH_GUARD_END
+}
+int hh_encoder_forward(hh_encoder* enc, const float* video, int B, float* fmap, void* stream) {
+  return hh_encoder_forward_n(enc, video, B, -1, fmap, stream);
+}
+double hh_encoder_flops_per_clip(const hh_encoder* enc) { return enc ? enc->impl.flops_per_clip() : 0.0; }
+int hh_encoder_last_launches(const hh_encoder* enc) { return enc ? enc->impl.launches : 0; }
+
+// ------------------------------------------------------------------------------------------ decoder
+int hh_decoder_create(hh_decoder** out, const hh_decoder_cfg* cfg) {
+  HH_GUARD_BEGIN
+  if (!out || !cfg) return fail(-2, "hh_decoder_create: null argument");
+  int rc = Decoder::validate(*cfg);
+  if (rc) return rc;
+  *out = new hh_decoder(*cfg);
+  return 0;
+  HH_GUARD_END
+}
+void hh_decoder_destroy(hh_decoder* dec) { delete dec; }
+int hh_decoder_set_weight(hh_decoder* dec, const char* key, const float* data, int64_t numel, void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_set_weight: null handle");
+  if (!key || !data) return fail(-2, "hh_decoder_set_weight: null argument");
+  return dec->impl.weights.set(key, data, numel, S(stream));
+  HH_GUARD_END
+}
+int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
+                       float* hs, float* logits, float* boxes, void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_forward: null handle");
+  return dec->impl.forward(features, stride_b, stride_row, B, T, hs, logits, boxes, S(stream));
+  HH_GUARD_END
+}
+double hh_decoder_flops_per_clip(const hh_decoder* dec, int T) { return dec ? dec->impl.flops_per_clip(T) : 0.0; }
+int hh_decoder_last_launches(const hh_decoder* dec) { return dec ? dec->impl.launches : 0; }
+
+// ------------------------------------------------------------------------------------------ stateless operators
+int hh_sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, void* stream) {
+  return sim_matrix(a, b, out, Na, Nb, d, eps, S(stream));
+}
+int hh_row_reduce(const float* x, int rows, int cols, float scale, int mode, void* out, void* stream) {
+  return row_reduce(x, rows, cols, scale, mode, out, S(stream));
+}
+int hh_l2_normalize(const float* x, float* out, int rows, int cols, float eps, void* stream) {
+  return l2_normalize_rows(x, out, rows, cols, eps, S(stream));
+}
+int hh_linear_f32(const float* in, int ldi, const float* in_add, int add_mod, const float* W, const float* bias,
+                  const float* residual, int ldres, float* out, int ldo, int R, int N, int K, int act, int in_relu,
+                  void* stream) {
+  LinArgs la{};
+  la.in = in; la.ldi = ldi; la.in_add = in_add; la.add_mod = add_mod; la.W = W; la.bias = bias;
+  la.residual = residual; la.ldres = ldres; la.out = out; la.ldo = ldo; la.R = R; la.N = N; la.K = K;
+  la.act = act; la.in_relu = in_relu;
+  return linear_f32(la, S(stream));
+}
+int hh_box_cxcywh_to_xyxy(const float* in, float* out, int64_t nboxes, void* stream) {
+  return box_cxcywh_to_xyxy(in, out, nboxes, S(stream));
+}
+int hh_box_xyxy_to_cxcywh(const float* in, float* out, int64_t nboxes, void* stream) {
+  return box_xyxy_to_cxcywh(in, out, nboxes, S(stream));
+}
+int hh_box_pairwise(const float* boxes1, const float* boxes2, int N, int M, float* iou, float* uni, float* giou,
+                    void* stream) {
+  return box_pairwise(boxes1, boxes2, N, M, iou, uni, giou, S(stream));
+}
+int hh_box_match_cost(const float* pred, const float* tgt, int N, int M, float w_bbox, float w_giou, float* cost,
+                      void* stream) {
+  return box_match_cost(pred, tgt, N, M, w_bbox, w_giou, cost, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------ kernel-level entry points
+int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
+                 const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream) {
+  return gemm_bf16(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, out, ldc, bias, residual, ldr, M,
+                   N, K, epilogue, S(stream));
+}
+int hh_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, float* out_f32, void* out_bf16,
+                 int M, int D, void* stream) {
+  LnArgs a{};
+  a.x = x; a.ldx = ldx; a.w = w; a.b = b; a.eps = eps; a.out_f32 = out_f32; a.out_bf16 = static_cast<bf16*>(out_bf16);
+  a.M = M; a.D = D;
+  return layernorm_rows(a, S(stream));
+}
+int hh_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  return f32_to_bf16(src, static_cast<bf16*>(dst), static_cast<size_t>(n), S(stream));
+}
+int hh_attention(const void* qkv, void* out, int B, int T, int n, int H, int kind, void* stream) {
+  const bf16* q = static_cast<const bf16*>(qkv);
+  bf16* o = static_cast<bf16*>(out);
+  switch (kind) {
+    case 0: return attn_space(q, o, B, T, n, H, S(stream));
+    case 1: return attn_time(q, o, B, T, n, H, S(stream));
+    case 2: return attn_cls(q, o, B, 1 + T * n, H, S(stream));
+  }
+  return fail(-2, "hh_attention: kind must be 0 (space), 1 (time) or 2 (cls)");
+}
+int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
+                       int S_, void* stream) {
+  HH_GUARD_BEGIN
+  static thread_local DevBuf ws;
+  int rc = ws.reserve(cross_attn_workspace_bytes(B, Q, heads, S_));
+  if (rc) return rc;
+  return cross_attn(q, static_cast<const bf16*>(K), static_cast<const bf16*>(V), ldkv, out, B, Q, heads, S_, ws.ptr,
+                    S(stream));
+  HH_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------ NCCL all-gather
+namespace {
+typedef int (*nccl_get_uid_t)(void*);
+struct HhNcclId {  // ncclUniqueId is passed BY VALUE to ncclCommInitRank: 128 opaque bytes
+  char internal[HH_NCCL_ID_BYTES];
+};
+typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_destroy_t)(void*);
+typedef const char* (*nccl_errstr_t)(int);
+
+struct NcclApi {
+  void* handle = nullptr;
+  nccl_get_uid_t get_uid = nullptr;
+  int (*init_rank)(void**, int, HhNcclId, int) = nullptr;
+  nccl_allgather_t allgather = nullptr;
+  nccl_destroy_t destroy = nullptr;
+  nccl_errstr_t errstr = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // RTLD_NOLOAD first: reuse the copy the host framework (torch) already mapped, so both share one NCCL.
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle)
+      for (const char* nm : names) {
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+      }
+    if (api.handle) {
+      api.get_uid = reinterpret_cast<nccl_get_uid_t>(dlsym(api.handle, "ncclGetUniqueId"));
+      api.init_rank = reinterpret_cast<int (*)(void**, int, HhNcclId, int)>(dlsym(api.handle, "ncclCommInitRank"));
+      api.allgather = reinterpret_cast<nccl_allgather_t>(dlsym(api.handle, "ncclAllGather"));
+      api.destroy = reinterpret_cast<nccl_destroy_t>(dlsym(api.handle, "ncclCommDestroy"));
+      api.errstr = reinterpret_cast<nccl_errstr_t>(dlsym(api.handle, "ncclGetErrorString"));
+    }
+  }
+  if (!api.handle || !api.get_uid || !api.init_rank || !api.allgather || !api.destroy) return nullptr;
+  return &api;
+}
+
+int nccl_fail(NcclApi* api, const char* what, int code) {
+  return fail(-3, std::string(what) + ": NCCL error " + std::to_string(code) +
+                      (api->errstr ? std::string(" (") + api->errstr(code) + ")" : std::string()));
+}
+}  // namespace
+
+int hh_comm_unique_id(void* id_host) {
+  NcclApi* api = nccl_api();
+  if (!api) return fail(-3, "hh_comm: libnccl.so.2 not found (load torch, or put NCCL on the library path)");
+  if (!id_host) return fail(-2, "hh_comm_unique_id: null buffer");
+  int rc = api->get_uid(id_host);
+  return rc ? nccl_fail(api, "ncclGetUniqueId", rc) : 0;
+}
+int hh_comm_create(void** comm, int nranks, int rank, const void* id_host) {
+  NcclApi* api = nccl_api();
+  if (!api) return fail(-3, "hh_comm: libnccl.so.2 not found (load torch, or put NCCL on the library path)");
+  if (!comm || !id_host || nranks < 1 || rank < 0 || rank >= nranks) return fail(-2, "hh_comm_create: bad argument");
+  HhNcclId id;
+  memcpy(id.internal, id_host, HH_NCCL_ID_BYTES);
+  int rc = api->init_rank(comm, nranks, id, rank);
+  return rc ? nccl_fail(api, "ncclCommInitRank", rc) : 0;
+}
+int hh_comm_destroy(void* comm) {
+  NcclApi* api = nccl_api();
+  if (!api || !comm) return 0;
+  int rc = api->destroy(comm);
+  return rc ? nccl_fail(api, "ncclCommDestroy", rc) : 0;
+}
+int hh_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream) {
+  NcclApi* api = nccl_api();
+  if (!api) return fail(-3, "hh_allgather: NCCL not available");
+  if (!comm || !send || !recv) return fail(-2, "hh_allgather: null argument");
+  // ncclInt8 == 0 : gather raw bytes so one packed buffer can carry mixed dtypes
+  int rc = api->allgather(send, recv, bytes_per_rank, /*ncclInt8*/ 0, comm, S(stream));
+  return rc ? nccl_fail(api, "ncclAllGather", rc) : 0;
+}
+
+}  // extern "C"

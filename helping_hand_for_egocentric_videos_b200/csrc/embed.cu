@@ -1,0 +1,131 @@
+// Encoder front end (model/LaviLa.py:218-223, 540-559):
+//   im2col_patches      video fp32 -> bf16 patch matrix so the 14x14/s14 (or 16x16/s16) bias-free conv becomes one
+//                       tcgen05 GEMM  [B*T*n, 3*p*p (padded)] x [D, 3*p*p]^T
+//   assemble_tokens_ln  prepend CLS, add the tiled spatial + repeated temporal position embeddings, apply ln_pre
+#include "hh_internal.h"
+#include "hh_ptx.cuh"
+
+namespace hh {
+
+namespace {
+
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ video, bf16* __restrict__ out, int BT,
+                                                     int H, int W, int p, int Kp) {
+  const int gw = W / p, gh = H / p;
+  const int n = gw * gh;
+  const int K = 3 * p * p;
+  const int half = Kp >> 1;
+  const long long total = static_cast<long long>(BT) * n * half;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % half) * 2;
+    const long long row = i / half;
+    const int patch = static_cast<int>(row % n);
+    const int img = static_cast<int>(row / n);
+    float v0 = 0.f, v1 = 0.f;
+    if (k < K) {  // p is even, so k and k+1 share (c, i)
+      const int c = k / (p * p);
+      const int rem = k - c * p * p;
+      const int ii = rem / p, jj = rem - ii * p;
+      const int py = patch / gw, px = patch - py * gw;
+      const float* s = video + ((static_cast<size_t>(img) * 3 + c) * H + (py * p + ii)) * W + px * p + jj;
+      const float2 t = *reinterpret_cast<const float2*>(s);
+      v0 = t.x;
+      v1 = t.y;
+    }
+    *reinterpret_cast<uint32_t*>(out + row * Kp + k) = pack_bf16x2(v0, v1);
+  }
+}
+
+constexpr int MAX_VEC = 8;
+
+__global__ void __launch_bounds__(256)
+assemble_ln_kernel(const float* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos,
+                   const float* __restrict__ temporal, const float* __restrict__ w, const float* __restrict__ b,
+                   float eps, float* __restrict__ x, int B, int T, int n, int D) {
+  const int N = 1 + T * n;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B * N) return;
+  const int bi = row / N, t = row - bi * N;
+  const int nv = D >> 7;
+  const float *src, *pe, *te = nullptr;
+  if (t == 0) {
+    src = cls;
+    pe = pos;
+  } else {
+    const int f = (t - 1) / n, q = (t - 1) - f * n;
+    src = tok + (static_cast<size_t>(bi) * T * n + (t - 1)) * D;
+    pe = pos + static_cast<size_t>(1 + q) * D;
+    te = temporal + static_cast<size_t>(f) * D;
+  }
+  float4 v[MAX_VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_VEC; ++j) {
+    if (j < nv) {
+      const int c = (j * 32 + lane) * 4;
+      float4 a = *reinterpret_cast<const float4*>(src + c);
+      float4 p4 = *reinterpret_cast<const float4*>(pe + c);
+      if (te) {  // reference sums (pos + temporal) first, then adds it to the token (LaviLa.py:553,557)
+        const float4 t4 = *reinterpret_cast<const float4*>(te + c);
+        p4.x += t4.x; p4.y += t4.y; p4.z += t4.z; p4.w += t4.w;
+      }
+      a.x += p4.x; a.y += p4.y; a.z += p4.z; a.w += p4.w;
+      v[j] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAX_VEC; ++j) {
+    if (j < nv) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      ss += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(D) + eps);
+  float* xr = x + static_cast<size_t>(row) * D;
+#pragma unroll
+  for (int j = 0; j < MAX_VEC; ++j) {
+    if (j < nv) {
+      const int c = (j * 32 + lane) * 4;
+      const float4 ww = *reinterpret_cast<const float4*>(w + c);
+      const float4 bb = *reinterpret_cast<const float4*>(b + c);
+      float4 y;
+      y.x = v[j].x * rstd * ww.x + bb.x;
+      y.y = v[j].y * rstd * ww.y + bb.y;
+      y.z = v[j].z * rstd * ww.z + bb.z;
+      y.w = v[j].w * rstd * ww.w + bb.w;
+      *reinterpret_cast<float4*>(xr + c) = y;
+    }
+  }
+}
+
+}  // namespace
+
+int im2col_patches(const float* video, bf16* out, int BT, int H, int W, int p, int Kp, cudaStream_t stream) {
+  HH_REQUIRE(p % 2 == 0 && H % p == 0 && W % p == 0, "im2col_patches: patch size must be even and divide H, W");
+  HH_REQUIRE(Kp % 8 == 0 && Kp >= 3 * p * p, "im2col_patches: padded K");
+  HH_REQUIRE((reinterpret_cast<uintptr_t>(video) & 7) == 0 && W % 2 == 0, "im2col_patches: video alignment");
+  const long long total = static_cast<long long>(BT) * (H / p) * (W / p) * (Kp / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  im2col_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(video, out, BT, H, W, p, Kp);
+  HH_CHECK_LAUNCH("im2col_kernel");
+  return 0;
+}
+
+int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, const float* temporal, const float* w,
+                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream) {
+  HH_REQUIRE(D % 128 == 0 && D <= 128 * MAX_VEC, "assemble_tokens_ln: D must be a multiple of 128, at most 1024");
+  const int rows = B * (1 + T * n);
+  const int grid = (rows + 7) / 8;
+  assemble_ln_kernel<<<grid, 256, 0, stream>>>(tok, cls, pos, temporal, w, b, eps, x, B, T, n, D);
+  HH_CHECK_LAUNCH("assemble_ln_kernel");
+  return 0;
+}
+
+}  // namespace hh

@@ -1,0 +1,522 @@
+// Encoder / decoder engines: own the packed weights and the workspace arena, sequence the kernels of one forward.
+// Host-side C++ only (no kernels here).  Reference call order: model/LaviLa.py:537-573 (encoder) and
+// model/tfm_decoder.py:183-233 (decoder); see DESIGN.md for the kernel-by-kernel mapping.
+#include "engine.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace hh {
+
+// ------------------------------------------------------------------------------------------ small utilities
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+DevBuf::~DevBuf() { release(); }
+void DevBuf::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+int DevBuf::reserve(size_t nbytes) {
+  if (nbytes <= bytes) return 0;
+  release();
+  cudaError_t e = cudaMalloc(&ptr, nbytes);
+  if (e != cudaSuccess) {
+    ptr = nullptr;
+    return fail(-3, std::string("cudaMalloc(") + std::to_string(nbytes) + "): " + cudaGetErrorString(e));
+  }
+  bytes = nbytes;
+  return 0;
+}
+
+int WeightStore::set(const std::string& key, const float* data, int64_t numel, cudaStream_t stream) {
+  auto it = expected.find(key);
+  if (it == expected.end()) return fail(-2, "unknown parameter key '" + key + "'");
+  if (it->second != numel)
+    return fail(-2, "parameter '" + key + "': expected " + std::to_string(it->second) + " elements, got " +
+                        std::to_string(numel));
+  DevBuf& b = bufs[key];
+  int rc = b.reserve(static_cast<size_t>(numel) * sizeof(float));
+  if (rc) return rc;
+  HH_CHECK_CUDA(cudaMemcpyAsync(b.ptr, data, static_cast<size_t>(numel) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  dirty = true;
+  return 0;
+}
+const float* WeightStore::get(const std::string& key) const {
+  auto it = bufs.find(key);
+  return it == bufs.end() ? nullptr : static_cast<const float*>(it->second.ptr);
+}
+int WeightStore::check_complete() const {
+  for (const auto& kv : expected)
+    if (bufs.find(kv.first) == bufs.end()) return fail(-2, "parameter '" + kv.first + "' was never set");
+  return 0;
+}
+
+#define RC(expr)          \
+  do {                    \
+    int _rc = (expr);     \
+    if (_rc) return _rc;  \
+  } while (0)
+
+// ========================================================================================== encoder
+Encoder::Encoder(const hh_encoder_cfg& c) : cfg(c) {
+  grid = cfg.img_size / cfg.patch_size;
+  n = grid * grid;
+  N = 1 + cfg.num_frames * n;
+  Kpatch = 3 * cfg.patch_size * cfg.patch_size;
+  Kp = (Kpatch + 63) / 64 * 64;
+  const int64_t D = cfg.embed_dim, Hd = cfg.mlp_hidden;
+  auto& e = weights.expected;
+  e["cls_token"] = D;
+  e["pos_embed"] = (n + 1) * D;
+  e["temporal_embed"] = cfg.num_frames * D;
+  e["patch_embed.proj.weight"] = D * Kpatch;
+  for (const char* nm : {"ln_pre", "norm"}) {
+    e[std::string(nm) + ".weight"] = D;
+    e[std::string(nm) + ".bias"] = D;
+  }
+  for (int i = 0; i < cfg.depth; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    for (const char* nm : {"norm1", "norm2", "norm3"}) {
+      e[p + nm + ".weight"] = D;
+      e[p + nm + ".bias"] = D;
+    }
+    for (const char* at : {"attn", "timeattn"}) {
+      e[p + at + ".qkv.weight"] = 3 * D * D;
+      e[p + at + ".qkv.bias"] = 3 * D;
+      e[p + at + ".proj.weight"] = D * D;
+      e[p + at + ".proj.bias"] = D;
+    }
+    e[p + "mlp.fc1.weight"] = Hd * D;
+    e[p + "mlp.fc1.bias"] = Hd;
+    e[p + "mlp.fc2.weight"] = D * Hd;
+    e[p + "mlp.fc2.bias"] = D;
+  }
+}
+
+int Encoder::validate(const hh_encoder_cfg& c) {
+  HH_REQUIRE(c.embed_dim % 128 == 0 && c.embed_dim <= 1024, "encoder: embed_dim must be a multiple of 128, <= 1024");
+  HH_REQUIRE(c.num_heads > 0 && c.embed_dim == c.num_heads * 64, "encoder: head dim must be 64");
+  HH_REQUIRE(c.patch_size > 0 && c.patch_size % 2 == 0 && c.img_size % c.patch_size == 0, "encoder: patch/img size");
+  HH_REQUIRE(c.num_frames >= 1 && c.num_frames <= 32, "encoder: 1..32 frames");
+  HH_REQUIRE(c.depth >= 1 && c.mlp_hidden % 64 == 0, "encoder: depth / mlp_hidden");
+  return 0;
+}
+
+int Encoder::pack(cudaStream_t s) {
+  RC(weights.check_complete());
+  const int D = cfg.embed_dim, Hd = cfg.mlp_hidden;
+  const float qscale = 1.0f / std::sqrt(64.0f);  // VarAttention.scale (LaviLa.py:233,252), folded into Wq / bq
+  RC(w_patch.reserve(static_cast<size_t>(D) * Kp * 2));
+  RC(pack_weight_bf16(weights.get("patch_embed.proj.weight"), static_cast<bf16*>(w_patch.ptr), D, Kpatch, Kp, 0, 1.f, s));
+  layers.resize(cfg.depth);
+  for (int i = 0; i < cfg.depth; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    Layer& L = layers[i];
+    const char* ats[2] = {"timeattn", "attn"};
+    for (int a = 0; a < 2; ++a) {
+      const std::string q = p + ats[a];
+      RC(L.w_qkv[a].reserve(static_cast<size_t>(3) * D * D * 2));
+      RC(pack_weight_bf16(weights.get(q + ".qkv.weight"), static_cast<bf16*>(L.w_qkv[a].ptr), 3 * D, D, D, D, qscale, s));
+      RC(L.b_qkv[a].reserve(static_cast<size_t>(3) * D * 4));
+      RC(scale_copy_f32(weights.get(q + ".qkv.bias"), static_cast<float*>(L.b_qkv[a].ptr), 3 * D, D, qscale, s));
+      RC(L.w_proj[a].reserve(static_cast<size_t>(D) * D * 2));
+      RC(pack_weight_bf16(weights.get(q + ".proj.weight"), static_cast<bf16*>(L.w_proj[a].ptr), D, D, D, 0, 1.f, s));
+    }
+    RC(L.w_fc1.reserve(static_cast<size_t>(Hd) * D * 2));
+    RC(pack_weight_bf16(weights.get(p + "mlp.fc1.weight"), static_cast<bf16*>(L.w_fc1.ptr), Hd, D, D, 0, 1.f, s));
+    RC(L.w_fc2.reserve(static_cast<size_t>(D) * Hd * 2));
+    RC(pack_weight_bf16(weights.get(p + "mlp.fc2.weight"), static_cast<bf16*>(L.w_fc2.ptr), D, Hd, Hd, 0, 1.f, s));
+  }
+  weights.dirty = false;
+  return 0;
+}
+
+int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaStream_t s) {
+  HH_REQUIRE(B > 0, "encoder forward: empty batch");
+  HH_REQUIRE(video != nullptr && fmap != nullptr, "encoder forward: null buffer");
+  if (weights.dirty) RC(pack(s));
+  if (nblocks < 0 || nblocks > cfg.depth) nblocks = cfg.depth;
+  launches = 0;
+  const int T = cfg.num_frames, D = cfg.embed_dim, H = cfg.num_heads, Hd = cfg.mlp_hidden;
+  const int chunk = B < max_chunk ? B : max_chunk;
+  // workspace for one chunk
+  const size_t Mc = static_cast<size_t>(chunk) * N;
+  const size_t Pc = static_cast<size_t>(chunk) * T * n;
+  RC(ws_patches.reserve(Pc * Kp * 2));
+  RC(ws_tok.reserve(Pc * D * 4));
+  RC(ws_x.reserve(Mc * D * 4));
+  RC(ws_tr.reserve(Mc * D * 4));
+  RC(ws_a.reserve(Mc * D * 2));
+  RC(ws_qkv.reserve(Mc * 3 * D * 2));
+  RC(ws_h.reserve(Mc * Hd * 2));
+  bf16* patches = static_cast<bf16*>(ws_patches.ptr);
+  float* tok = static_cast<float*>(ws_tok.ptr);
+  float* x = static_cast<float*>(ws_x.ptr);
+  float* tr = static_cast<float*>(ws_tr.ptr);
+  bf16* a = static_cast<bf16*>(ws_a.ptr);
+  bf16* qkv = static_cast<bf16*>(ws_qkv.ptr);
+  bf16* h = static_cast<bf16*>(ws_h.ptr);
+  const size_t frame_elems = static_cast<size_t>(3) * cfg.img_size * cfg.img_size;
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int Bc = (B - b0) < chunk ? (B - b0) : chunk;
+    const int M = Bc * N;
+    const int P = Bc * T * n;
+    const float* vid = video + static_cast<size_t>(b0) * T * frame_elems;
+    // patch embed (LaviLa.py:218-223,540-542) + CLS/pos/temporal + ln_pre (:545-559)
+    RC(im2col_patches(vid, patches, Bc * T, cfg.img_size, cfg.img_size, cfg.patch_size, Kp, s));
+    RC(gemm_bf16(patches, Kp, static_cast<const bf16*>(w_patch.ptr), Kp, tok, D, nullptr, nullptr, 0, P, D, Kp,
+                 EPI_BIAS_F32, s));
+    RC(assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
+                          weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
+    launches += 3;
+    for (int i = 0; i < nblocks; ++i) {
+      const std::string p = "blocks." + std::to_string(i) + ".";
+      const Layer& L = layers[i];
+      for (int at = 0; at < 2; ++at) {  // 0 = time (norm3 on x), 1 = space (norm1 on x + time_out)
+        const std::string nm = p + (at == 0 ? "norm3" : "norm1");
+        const std::string q = p + (at == 0 ? "timeattn" : "attn");
+        LnArgs ln{};
+        ln.x = (at == 0) ? x : tr;
+        ln.ldx = D;
+        ln.w = weights.get(nm + ".weight");
+        ln.b = weights.get(nm + ".bias");
+        ln.eps = 1e-6f;
+        ln.out_bf16 = a;
+        ln.M = M;
+        ln.D = D;
+        RC(layernorm_rows(ln, s));
+        RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
+                     static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
+        if (at == 0) RC(attn_time(qkv, a, Bc, T, n, H, s));
+        else RC(attn_space(qkv, a, Bc, T, n, H, s));
+        RC(attn_cls(qkv, a, Bc, N, H, s));
+        // time: tr = x + proj(o)  (:364) ; space: x <- x + proj(o)  (:384, 'frozen-in-time': x, not tr)
+        RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, (at == 0) ? tr : x, D,
+                     weights.get(q + ".proj.bias"), x, D, M, D, D, EPI_BIAS_RES_F32, s));
+        launches += 5;
+      }
+      LnArgs ln{};
+      ln.x = x;
+      ln.ldx = D;
+      ln.w = weights.get(p + "norm2.weight");
+      ln.b = weights.get(p + "norm2.bias");
+      ln.eps = 1e-6f;
+      ln.out_bf16 = a;
+      ln.M = M;
+      ln.D = D;
+      RC(layernorm_rows(ln, s));
+      RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_fc1.ptr), D, h, Hd, weights.get(p + "mlp.fc1.bias"), nullptr, 0, M,
+                   Hd, D, EPI_BIAS_QGELU_BF16, s));
+      RC(gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, x, D, weights.get(p + "mlp.fc2.bias"), x, D, M, D,
+                   Hd, EPI_BIAS_RES_F32, s));
+      launches += 3;
+    }
+    LnArgs ln{};
+    ln.x = x;
+    ln.ldx = D;
+    ln.w = weights.get("norm.weight");
+    ln.b = weights.get("norm.bias");
+    ln.eps = 1e-6f;
+    ln.out_f32 = fmap + static_cast<size_t>(b0) * N * D;
+    ln.M = M;
+    ln.D = D;
+    RC(layernorm_rows(ln, s));
+    launches += 1;
+  }
+  return 0;
+}
+
+double Encoder::flops_per_clip() const {
+  // F_enc = 2 nT 3p^2 D + L [32 N D^2 + 4 D (n T (T+1) + N) + 4 D (T n (n+1) + N)] + 2 D 256
+  const double D = cfg.embed_dim, T = cfg.num_frames, nn = n, NN = N, L = cfg.depth;
+  const double ratio = static_cast<double>(cfg.mlp_hidden) / cfg.embed_dim;
+  const double lin = (8.0 + 4.0 * ratio) * NN * D * D;  // qkv x2 (12) + proj x2 (4) + mlp (4*ratio), x2 flops -> 32 at ratio 4
+  return 2.0 * nn * T * Kpatch * D + L * (lin + 4.0 * D * (nn * T * (T + 1) + NN) + 4.0 * D * (T * nn * (nn + 1) + NN)) +
+         2.0 * D * 256.0;
+}
+
+// ========================================================================================== decoder
+Decoder::Decoder(const hh_decoder_cfg& c) : cfg(c) {
+  const int64_t C = cfg.d_model, Fd = cfg.dim_feedforward;
+  auto& e = weights.expected;
+  e["pos_embed"] = (cfg.patches_per_frame + 1) * C;
+  e["temporal_embed"] = cfg.num_frames * C;
+  e["transformer.pre_norm.weight"] = C;
+  e["transformer.pre_norm.bias"] = C;
+  e["transformer.decoder.norm.weight"] = C;
+  e["transformer.decoder.norm.bias"] = C;
+  e["class_embed.weight"] = static_cast<int64_t>(cfg.num_classes1) * C;
+  e["class_embed.bias"] = cfg.num_classes1;
+  e["query_embed.weight"] = cfg.num_queries * C;
+  e["proj.weight"] = C * cfg.feature_dim;
+  const int64_t dims[4] = {C, C, C, 4};
+  for (int j = 0; j < 3; ++j) {
+    e["bbox_embed.layers." + std::to_string(j) + ".weight"] = dims[j + 1] * dims[j];
+    e["bbox_embed.layers." + std::to_string(j) + ".bias"] = dims[j + 1];
+  }
+  if (cfg.pred_traj) {
+    e["frame_index.weight"] = cfg.num_frames * C;
+    e["frame_proj.weight"] = C * 2 * C;
+    e["frame_proj.bias"] = C;
+  }
+  for (int i = 0; i < cfg.num_layers; ++i) {
+    const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
+    for (const char* at : {"multihead_attn", "self_attn"}) {
+      e[p + at + ".in_proj_weight"] = 3 * C * C;
+      e[p + at + ".in_proj_bias"] = 3 * C;
+      e[p + at + ".out_proj.weight"] = C * C;
+      e[p + at + ".out_proj.bias"] = C;
+    }
+    e[p + "linear1.weight"] = Fd * C;
+    e[p + "linear1.bias"] = Fd;
+    e[p + "linear2.weight"] = C * Fd;
+    e[p + "linear2.bias"] = C;
+    for (const char* nm : {"norm1", "norm2", "norm3"}) {
+      e[p + nm + ".weight"] = C;
+      e[p + nm + ".bias"] = C;
+    }
+  }
+}
+
+int Decoder::validate(const hh_decoder_cfg& c) {
+  HH_REQUIRE(c.d_model % 128 == 0 && c.d_model <= 1024, "decoder: d_model must be a multiple of 128, <= 1024");
+  HH_REQUIRE(c.nhead > 0 && c.d_model == c.nhead * 64, "decoder: head dim must be 64");
+  HH_REQUIRE(c.num_queries >= 1 && c.num_queries <= 16, "decoder: 1..16 queries (num_queries==1 n_decode path unsupported)");
+  HH_REQUIRE(c.num_layers >= 1 && c.dim_feedforward % 32 == 0, "decoder: layers / ffn");
+  HH_REQUIRE(c.feature_dim % 8 == 0 && c.num_classes1 % 4 == 0, "decoder: feature_dim % 8, (num_classes+1) % 4");
+  HH_REQUIRE(c.num_frames >= 1 && c.patches_per_frame >= 1, "decoder: frames / patches");
+  return 0;
+}
+
+int Decoder::pack(cudaStream_t s) {
+  RC(weights.check_complete());
+  const int C = cfg.d_model, Lr = cfg.num_layers, F = cfg.feature_dim;
+  const float qscale = 1.0f / std::sqrt(64.0f);  // nn.MultiheadAttention scales q by head_dim^-0.5
+  RC(w_proj.reserve(static_cast<size_t>(C) * F * 2));
+  RC(pack_weight_bf16(weights.get("proj.weight"), static_cast<bf16*>(w_proj.ptr), C, F, F, 0, 1.f, s));
+  RC(w_cls.reserve(static_cast<size_t>(cfg.num_classes1) * C * 2));
+  RC(pack_weight_bf16(weights.get("class_embed.weight"), static_cast<bf16*>(w_cls.ptr), cfg.num_classes1, C, C, 0, 1.f, s));
+  // memory is layer-invariant: the 6 layers' cross-attention K (resp. V) projections become ONE GEMM each
+  RC(w_kall.reserve(static_cast<size_t>(Lr) * C * C * 2));
+  RC(w_vall.reserve(static_cast<size_t>(Lr) * C * C * 2));
+  RC(b_kall.reserve(static_cast<size_t>(Lr) * C * 4));
+  RC(b_vall.reserve(static_cast<size_t>(Lr) * C * 4));
+  RC(w_sa.reserve(static_cast<size_t>(Lr) * 3 * C * C * 4));
+  RC(b_sa.reserve(static_cast<size_t>(Lr) * 3 * C * 4));
+  RC(w_caq.reserve(static_cast<size_t>(Lr) * C * C * 4));
+  RC(b_caq.reserve(static_cast<size_t>(Lr) * C * 4));
+  for (int i = 0; i < Lr; ++i) {
+    const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
+    const float* wca = weights.get(p + "multihead_attn.in_proj_weight");
+    const float* bca = weights.get(p + "multihead_attn.in_proj_bias");
+    RC(pack_weight_bf16(wca + static_cast<size_t>(C) * C, static_cast<bf16*>(w_kall.ptr) + static_cast<size_t>(i) * C * C, C, C,
+                        C, 0, 1.f, s));
+    RC(pack_weight_bf16(wca + static_cast<size_t>(2) * C * C, static_cast<bf16*>(w_vall.ptr) + static_cast<size_t>(i) * C * C,
+                        C, C, C, 0, 1.f, s));
+    RC(scale_copy_f32(bca + C, static_cast<float*>(b_kall.ptr) + static_cast<size_t>(i) * C, C, 0, 1.f, s));
+    RC(scale_copy_f32(bca + 2 * C, static_cast<float*>(b_vall.ptr) + static_cast<size_t>(i) * C, C, 0, 1.f, s));
+    RC(scale_copy_f32(wca, static_cast<float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C, static_cast<size_t>(C) * C,
+                      static_cast<size_t>(C) * C, qscale, s));
+    RC(scale_copy_f32(bca, static_cast<float*>(b_caq.ptr) + static_cast<size_t>(i) * C, C, C, qscale, s));
+    RC(scale_copy_f32(weights.get(p + "self_attn.in_proj_weight"), static_cast<float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C,
+                      static_cast<size_t>(3) * C * C, static_cast<size_t>(C) * C, qscale, s));
+    RC(scale_copy_f32(weights.get(p + "self_attn.in_proj_bias"), static_cast<float*>(b_sa.ptr) + static_cast<size_t>(i) * 3 * C,
+                      3 * C, C, qscale, s));
+  }
+  // constant 3-D position embedding (tfm_decoder.py:161-166)
+  const int S = cfg.num_frames * cfg.patches_per_frame;
+  RC(pos3d.reserve(static_cast<size_t>(S) * C * 4));
+  RC(build_pos3d(weights.get("pos_embed"), weights.get("temporal_embed"), static_cast<float*>(pos3d.ptr), cfg.num_frames,
+                 cfg.patches_per_frame, C, s));
+  if (cfg.pred_traj) {
+    // frame_proj([hs ; frame_index[t]]) = hs W1^T + (frame_index[t] W2^T + b)   (tfm_decoder.py:212-215)
+    RC(w_f1.reserve(static_cast<size_t>(C) * C * 4));
+    RC(w_f2.reserve(static_cast<size_t>(C) * C * 4));
+    RC(frameterm.reserve(static_cast<size_t>(cfg.num_frames) * C * 4));
+    RC(slice_cols_f32(weights.get("frame_proj.weight"), 2 * C, 0, static_cast<float*>(w_f1.ptr), C, C, s));
+    RC(slice_cols_f32(weights.get("frame_proj.weight"), 2 * C, C, static_cast<float*>(w_f2.ptr), C, C, s));
+    LinArgs la{};
+    la.in = weights.get("frame_index.weight");
+    la.ldi = C;
+    la.W = static_cast<const float*>(w_f2.ptr);
+    la.bias = weights.get("frame_proj.bias");
+    la.out = static_cast<float*>(frameterm.ptr);
+    la.ldo = C;
+    la.R = cfg.num_frames;
+    la.N = C;
+    la.K = C;
+    RC(linear_f32(la, s));
+  }
+  weights.dirty = false;
+  return 0;
+}
+
+static int lin(const float* in, int ldi, const float* in_add, int add_mod, const float* W, const float* bias,
+               const float* residual, int ldres, float* out, int ldo, int R, int N, int K, int act, cudaStream_t s) {
+  LinArgs la{};
+  la.in = in; la.ldi = ldi; la.in_add = in_add; la.add_mod = add_mod; la.W = W; la.bias = bias;
+  la.residual = residual; la.ldres = ldres; la.out = out; la.ldo = ldo; la.R = R; la.N = N; la.K = K; la.act = act;
+  return linear_f32(la, s);
+}
+
+int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row, int B, int T, float* hs, float* logits,
+                     float* boxes, cudaStream_t s) {
+  HH_REQUIRE(B > 0 && features && hs && logits && boxes, "decoder forward: bad arguments");
+  HH_REQUIRE(T == cfg.num_frames, "decoder forward: T must equal num_frames (construct_3d_pos_embed, tfm_decoder.py:161-166)");
+  if (weights.dirty) RC(pack(s));
+  launches = 0;
+  const int C = cfg.d_model, Lr = cfg.num_layers, F = cfg.feature_dim, Q = cfg.num_queries, Fd = cfg.dim_feedforward;
+  const int n = cfg.patches_per_frame, S = T * n, heads = cfg.nhead, ncls = cfg.num_classes1;
+  const int R = B * Q;
+  const size_t BS = static_cast<size_t>(B) * S;
+  RC(ws_feat.reserve(BS * F * 2));
+  RC(ws_memf.reserve(BS * C * 4));
+  RC(ws_mem.reserve(BS * C * 2));
+  RC(ws_mempos.reserve(BS * C * 2));
+  RC(ws_k.reserve(BS * Lr * C * 2));
+  RC(ws_v.reserve(BS * Lr * C * 2));
+  RC(ws_q.reserve(static_cast<size_t>(R) * (3 * C /*tgt,t2,o*/ + 3 * C /*qkv*/ + Fd) * 4));
+  RC(ws_cross.reserve(cross_attn_workspace_bytes(B, Q, heads, S)));
+  const bool traj = cfg.pred_traj && T == cfg.num_frames;
+  const size_t LR = static_cast<size_t>(Lr) * R;
+  RC(ws_head.reserve((LR * C * 2 /*bf16 hs*/) + LR * C * 4 /*hsproj*/ + LR * (traj ? T : 1) * C * 4 * 3 /*cond,x1,x2*/ +
+                     (traj ? LR * static_cast<size_t>(ncls) * 4 : 0)));
+
+  bf16* feat = static_cast<bf16*>(ws_feat.ptr);
+  float* memf = static_cast<float*>(ws_memf.ptr);
+  bf16* mem = static_cast<bf16*>(ws_mem.ptr);
+  bf16* mempos = static_cast<bf16*>(ws_mempos.ptr);
+  bf16* Kall = static_cast<bf16*>(ws_k.ptr);
+  bf16* Vall = static_cast<bf16*>(ws_v.ptr);
+  float* tgt = static_cast<float*>(ws_q.ptr);
+  float* t2 = tgt + static_cast<size_t>(R) * C;
+  float* o = t2 + static_cast<size_t>(R) * C;
+  float* qkv = o + static_cast<size_t>(R) * C;
+  float* ffn = qkv + static_cast<size_t>(R) * 3 * C;
+  const float* qpos = weights.get("query_embed.weight");
+
+  // proj (no bias, :200) -> pre_norm (:86) ; memory and memory+pos in bf16 for the K/V GEMMs
+  RC(cast_rows_bf16(features, stride_b, stride_row, S, feat, static_cast<int>(BS), F, s));
+  RC(gemm_bf16(feat, F, static_cast<const bf16*>(w_proj.ptr), F, memf, C, nullptr, nullptr, 0, static_cast<int>(BS), C, F,
+               EPI_BIAS_F32, s));
+  LnArgs ln{};
+  ln.x = memf; ln.ldx = C;
+  ln.w = weights.get("transformer.pre_norm.weight"); ln.b = weights.get("transformer.pre_norm.bias"); ln.eps = 1e-5f;
+  ln.out_bf16 = mem;
+  ln.post_add = static_cast<const float*>(pos3d.ptr); ln.post_mod = S; ln.out2_bf16 = mempos;
+  ln.M = static_cast<int>(BS); ln.D = C;
+  RC(layernorm_rows(ln, s));
+  RC(gemm_bf16(mempos, C, static_cast<const bf16*>(w_kall.ptr), C, Kall, Lr * C, static_cast<const float*>(b_kall.ptr),
+               nullptr, 0, static_cast<int>(BS), Lr * C, C, EPI_BIAS_BF16, s));
+  RC(gemm_bf16(mem, C, static_cast<const bf16*>(w_vall.ptr), C, Vall, Lr * C, static_cast<const float*>(b_vall.ptr), nullptr,
+               0, static_cast<int>(BS), Lr * C, C, EPI_BIAS_BF16, s));
+  HH_CHECK_CUDA(cudaMemsetAsync(tgt, 0, static_cast<size_t>(R) * C * 4, s));  // tgt = zeros (:84)
+  launches += 6;
+
+  auto lnq = [&](const float* x, const std::string& nm, float* out) {
+    LnArgs a{};
+    a.x = x; a.ldx = C; a.w = weights.get(nm + ".weight"); a.b = weights.get(nm + ".bias"); a.eps = 1e-5f;
+    a.out_f32 = out; a.M = R; a.D = C;
+    return layernorm_rows(a, s);
+  };
+  for (int i = 0; i < Lr; ++i) {
+    const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
+    const float* wsa = static_cast<const float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C;
+    const float* bsa = static_cast<const float*>(b_sa.ptr) + static_cast<size_t>(i) * 3 * C;
+    // self attention over the queries (:431-435)
+    RC(lnq(tgt, p + "norm1", t2));
+    RC(lin(t2, C, qpos, Q, wsa, bsa, nullptr, 0, qkv, 3 * C, R, 2 * C, C, 0, s));                       // q,k <- t2+qpos
+    RC(lin(t2, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, qkv + 2 * C, 3 * C, R, C, C, 0, s));
+    RC(self_attn_queries(qkv, qkv + C, qkv + 2 * C, 3 * C, o, B, Q, heads, s));
+    RC(lin(o, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), tgt, C,
+           tgt, C, R, C, C, 0, s));
+    // cross attention to the patch tokens (:436-441,456)
+    RC(lnq(tgt, p + "norm2", t2));
+    RC(lin(t2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
+           static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, qkv, C, R, C, C, 0, s));
+    RC(cross_attn(qkv, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, o, B, Q, heads, S,
+                  ws_cross.ptr, s));
+    RC(lin(o, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
+           tgt, C, tgt, C, R, C, C, 0, s));
+    // FFN (:457-459)
+    RC(lnq(tgt, p + "norm3", t2));
+    RC(lin(t2, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, ffn, Fd, R, Fd, C,
+           1, s));
+    RC(lin(ffn, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), tgt, C, tgt, C, R, C, Fd, 0,
+           s));
+    // intermediate output through the shared final norm (:282,287-291)
+    RC(lnq(tgt, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
+    launches += 15;
+  }
+
+  // ---- heads
+  uint8_t* hp = static_cast<uint8_t*>(ws_head.ptr);
+  bf16* hs16 = reinterpret_cast<bf16*>(hp);
+  hp += LR * C * 2;
+  float* hsproj = reinterpret_cast<float*>(hp);
+  hp += LR * C * 4;
+  const size_t rows_box = LR * (traj ? T : 1);
+  float* cond = reinterpret_cast<float*>(hp);
+  hp += rows_box * C * 4;
+  float* x1 = reinterpret_cast<float*>(hp);
+  hp += rows_box * C * 4;
+  float* x2 = reinterpret_cast<float*>(hp);
+  hp += rows_box * C * 4;
+  float* logits_raw = traj ? reinterpret_cast<float*>(hp) : logits;
+
+  RC(f32_to_bf16(hs, hs16, LR * C, s));
+  RC(gemm_bf16(hs16, C, static_cast<const bf16*>(w_cls.ptr), C, logits_raw, ncls, weights.get("class_embed.bias"), nullptr, 0,
+               static_cast<int>(LR), ncls, C, EPI_BIAS_F32, s));  // class_embed (:208)
+  launches += 2;
+  const float* box_in = hs;
+  if (traj) {
+    RC(expand_logits(logits_raw, logits, Lr * B, 4, static_cast<size_t>(Q) * ncls, s));  // literal 4 (:216)
+    RC(lin(hs, C, nullptr, 0, static_cast<const float*>(w_f1.ptr), nullptr, nullptr, 0, hsproj, C, static_cast<int>(LR), C, C, 0, s));
+    RC(add_frame_term(hsproj, static_cast<const float*>(frameterm.ptr), cond, Lr * B, T, Q, C, s));
+    box_in = cond;
+    launches += 3;
+  }
+  // bbox_embed: 3-layer MLP + sigmoid (:228)
+  RC(lin(box_in, C, nullptr, 0, weights.get("bbox_embed.layers.0.weight"), weights.get("bbox_embed.layers.0.bias"), nullptr, 0, x1,
+         C, static_cast<int>(rows_box), C, C, 1, s));
+  RC(lin(x1, C, nullptr, 0, weights.get("bbox_embed.layers.1.weight"), weights.get("bbox_embed.layers.1.bias"), nullptr, 0, x2, C,
+         static_cast<int>(rows_box), C, C, 1, s));
+  RC(lin(x2, C, nullptr, 0, weights.get("bbox_embed.layers.2.weight"), weights.get("bbox_embed.layers.2.bias"), nullptr, 0, boxes,
+         4, static_cast<int>(rows_box), 4, C, 2, s));
+  launches += 3;
+  return 0;
+}
+
+double Decoder::flops_per_clip(int T) const {
+  // F_dec
+  const double C = cfg.d_model, S = static_cast<double>(T) * cfg.patches_per_frame, Q = cfg.num_queries, F = cfg.feature_dim;
+  const double Lr = cfg.num_layers, ffn = cfg.dim_feedforward, ncls = cfg.num_classes1;
+  const bool traj = cfg.pred_traj && T == cfg.num_frames;
+  const double Rr = Lr * Q * (traj ? T : 1);
+  double fl = 2 * S * F * C + Lr * (4 * S * C * C + 4 * Q * S * C + (12 * Q * C * C + 4 * Q * Q * C) + 4 * Q * C * ffn) +
+              Lr * 2 * Q * C * ncls + Rr * 2 * (2 * C * C + 4 * C) + 2 * Q * (C * C + 256 * C);
+  if (traj) fl += Rr * 2 * 2 * C * C;
+  return fl;
+}
+
+}  // namespace hh

@@ -1,0 +1,70 @@
+// Engine objects behind the opaque hh_encoder / hh_decoder handles of include/hh_b200.h.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hh_b200.h"
+#include "hh_internal.h"
+
+namespace hh {
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), bytes(o.bytes) { o.ptr = nullptr; o.bytes = 0; }
+  ~DevBuf();
+  int reserve(size_t nbytes);  // grow-only
+  void release();
+};
+
+// fp32 master copies of the module's parameters, keyed by reference state_dict name.
+struct WeightStore {
+  std::map<std::string, int64_t> expected;  // key -> numel
+  std::map<std::string, DevBuf> bufs;
+  bool dirty = true;
+  int set(const std::string& key, const float* data, int64_t numel, cudaStream_t stream);
+  const float* get(const std::string& key) const;
+  int check_complete() const;
+};
+
+struct Encoder {
+  hh_encoder_cfg cfg;
+  int grid, n, N, Kpatch, Kp;
+  int max_chunk = 64;  // clips per pass through the workspace
+  int launches = 0;
+  WeightStore weights;
+  struct Layer {
+    DevBuf w_qkv[2], b_qkv[2], w_proj[2];  // [0] = timeattn, [1] = attn (space)
+    DevBuf w_fc1, w_fc2;
+  };
+  std::vector<Layer> layers;
+  DevBuf w_patch;
+  DevBuf ws_patches, ws_tok, ws_x, ws_tr, ws_a, ws_qkv, ws_h;
+
+  explicit Encoder(const hh_encoder_cfg& c);
+  static int validate(const hh_encoder_cfg& c);
+  int pack(cudaStream_t s);
+  int forward(const float* video, int B, int nblocks, float* fmap, cudaStream_t s);
+  double flops_per_clip() const;
+};
+
+struct Decoder {
+  hh_decoder_cfg cfg;
+  int launches = 0;
+  WeightStore weights;
+  DevBuf w_proj, w_cls, w_kall, w_vall, b_kall, b_vall, w_sa, b_sa, w_caq, b_caq, pos3d, w_f1, w_f2, frameterm;
+  DevBuf ws_feat, ws_memf, ws_mem, ws_mempos, ws_k, ws_v, ws_q, ws_cross, ws_head;
+
+  explicit Decoder(const hh_decoder_cfg& c);
+  static int validate(const hh_decoder_cfg& c);
+  int pack(cudaStream_t s);
+  int forward(const float* features, int64_t stride_b, int64_t stride_row, int B, int T, float* hs, float* logits,
+              float* boxes, cudaStream_t s);
+  double flops_per_clip(int T) const;
+};
+
+}  // namespace hh

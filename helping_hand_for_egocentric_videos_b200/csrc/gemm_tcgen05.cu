@@ -1,0 +1,372 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+//   * operands: TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a ring of shared-memory stages
+//   * math:     tcgen05.mma (cta_group::1, 128 x BLOCK_N x 16 per instruction) issued by ONE thread, fp32
+//               accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps
+//               the MMAs of tile i+1
+//   * epilogue: 4 warps: tcgen05.ld -> registers -> bias / QuickGELU -> per-warp smem transpose -> coalesced
+//               128-byte row stores (bf16) or fp32 rows with the fp32 residual added
+//
+// This one kernel carries every encoder contraction of the reference -- qkv / proj / fc1 / fc2 nn.Linear calls in
+// model/LaviLa.py:249,281,186,189 -- plus the patch-embed conv as an im2col GEMM (:216-223), the decoder's memory
+// projections (model/tfm_decoder.py:200,438-441) and class head (:208).
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..7 = epilogue.
+#include "hh_internal.h"
+#include "hh_ptx.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace hh {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int STAGE_LD = 33;  // per-warp transpose buffer: 32 rows x 33 words
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int EPI_BYTES = 4 * 32 * STAGE_LD * 4;
+  static constexpr int BIAS_BYTES = BLOCK_N * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: power of two
+};
+
+struct GemmArgs {
+  void* out;
+  const float* bias;
+  const float* residual;
+  int M, N, K;
+  int ldc, ldr;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ float quick_gelu(float x) {
+  // x * sigmoid(1.702 x)   (model/openai_model.py:177-179)
+  return __fdividef(x, 1.0f + __expf(-1.702f * x));
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint8_t* stage_base = smem;
+  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::BIAS_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;      // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile - m_blk * p.tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance K inside the 128-byte swizzle row: +32 bytes => +2 in (addr >> 4) units
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    float* st = epi_stage + q * 32 * STAGE_LD;
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile - m_blk * p.tiles_n;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int col0 = n_blk * BLOCK_N;
+
+      // bias tile -> smem (previous tile's readers are done: they passed the trailing named barrier)
+      for (int c = et; c < BLOCK_N; c += 128) {
+        const int col = col0 + c;
+        bias_s[c] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+
+      if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll 1
+        for (int g = 0; g < BLOCK_N / 64; ++g) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(g * 64 + h * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float v0 = __uint_as_float(r[j]) + bias_s[g * 64 + h * 32 + j];
+              float v1 = __uint_as_float(r[j + 1]) + bias_s[g * 64 + h * 32 + j + 1];
+              if constexpr (EPI == EPI_BIAS_QGELU_BF16) {
+                v0 = quick_gelu(v0);
+                v1 = quick_gelu(v1);
+              }
+              // thread = row `lane`; word index = column pair
+              reinterpret_cast<uint32_t*>(st)[lane * STAGE_LD + h * 16 + (j >> 1)] = pack_bf16x2(v0, v1);
+            }
+          }
+          __syncwarp();
+          // row i of this warp's 32 rows: 32 lanes x 4 bytes = 128 contiguous bytes (64 bf16 columns)
+          const int colw = col0 + g * 64 + lane * 2;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int row = row0 + i;
+            const uint32_t w = reinterpret_cast<uint32_t*>(st)[i * STAGE_LD + lane];
+            if (row < p.M) {
+              __nv_bfloat16* dst = out + static_cast<size_t>(row) * p.ldc + colw;
+              if (colw + 1 < p.N) {
+                *reinterpret_cast<uint32_t*>(dst) = w;
+              } else if (colw < p.N) {
+                dst[0] = __ushort_as_bfloat16(static_cast<unsigned short>(w & 0xFFFFu));
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+        for (int g = 0; g < BLOCK_N / 32; ++g) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(g * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * STAGE_LD + j] = __uint_as_float(r[j]) + bias_s[g * 32 + j];
+          __syncwarp();
+          const int col = col0 + g * 32 + lane;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int row = row0 + i;
+            float v = st[i * STAGE_LD + lane];
+            if (row < p.M && col < p.N) {
+              if constexpr (EPI == EPI_BIAS_RES_F32) v += p.residual[static_cast<size_t>(row) * p.ldr + col];
+              out[static_cast<size_t>(row) * p.ldc + col] = v;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above) -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias_s free for the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (cols contiguous, row stride ld elements); box = [BLOCK_K cols, box_rows rows].
+int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+template <int BLOCK_N, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool configured = false;
+  auto kern = gemm_kernel<BLOCK_N, EPI>;
+  if (!configured) {
+    HH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = args.tiles_m * args.tiles_n;
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, args);
+  HH_CHECK_LAUNCH("gemm_kernel");
+  return 0;
+}
+
+template <int BLOCK_N>
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int epi, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16>(ta, tb, args, stream);
+    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16>(ta, tb, args, stream);
+    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32>(ta, tb, args, stream);
+    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32>(ta, tb, args, stream);
+  }
+  return fail(-2, "gemm_bf16: unknown epilogue");
+}
+
+}  // namespace
+
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
+              const float* residual, int ldr, int M, int N, int K, int epilogue, cudaStream_t stream) {
+  HH_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem");
+  HH_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: lda/ldw must be multiples of 8 elements (16-byte TMA strides)");
+  HH_REQUIRE(K % 8 == 0, "gemm_bf16: K must be a multiple of 8");
+  HH_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+             "gemm_bf16: A and W must be 16-byte aligned");
+  const bool out_bf16 = (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_QGELU_BF16);
+  if (out_bf16) {
+    HH_REQUIRE(ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "gemm_bf16: bf16 output needs even ldc");
+  }
+  if (epilogue == EPI_BIAS_RES_F32) HH_REQUIRE(residual != nullptr, "gemm_bf16: residual epilogue without residual");
+
+  // Tile width: 256 for the wide encoder GEMMs; 128 when N is small or the 256-wide grid would leave SMs idle.
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  int bn = 256;
+  if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || tiles_m * ((N + 255) / 256) < num_sms()) bn = 128;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tb, W, N, K, ldw, bn);
+  if (rc) return rc;
+
+  GemmArgs args;
+  args.out = out;
+  args.bias = bias;
+  args.residual = residual;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.ldc = ldc;
+  args.ldr = ldr;
+  args.tiles_m = tiles_m;
+  args.tiles_n = (N + bn - 1) / bn;
+  if (bn == 256) return dispatch_epi<256>(ta, tb, args, epilogue, stream);
+  return dispatch_epi<128>(ta, tb, args, epilogue, stream);
+}
+
+}  // namespace hh

@@ -1,0 +1,132 @@
+// Internal (C++) interface between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace hh {
+
+typedef __nv_bfloat16 bf16;
+
+// Thread-local last error (reported through hh_last_error()).
+void set_error(const std::string& msg);
+const char* last_error_cstr();
+int fail(int code, const std::string& msg);  // records msg, returns code
+
+#define HH_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::hh::fail(-3, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+
+#define HH_CHECK_LAUNCH(name)                                                                       \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) return ::hh::fail(-3, std::string(name) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define HH_REQUIRE(cond, msg)                                         \
+  do {                                                                \
+    if (!(cond)) return ::hh::fail(-2, std::string(msg) + " [" #cond "]"); \
+  } while (0)
+
+int num_sms();
+
+// ---------------------------------------------------------------- GEMM (gemm_tcgen05.cu)
+enum GemmEpilogue {
+  EPI_BIAS_BF16 = 0,        // out bf16 = acc + bias
+  EPI_BIAS_QGELU_BF16 = 1,  // out bf16 = quickgelu(acc + bias)
+  EPI_BIAS_RES_F32 = 2,     // out f32  = acc + bias + residual (residual may alias out)
+  EPI_BIAS_F32 = 3,         // out f32  = acc + bias
+};
+// C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W bf16 with K contiguous. bias fp32 [N] or nullptr.
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
+              const float* residual, int ldr, int M, int N, int K, int epilogue, cudaStream_t stream);
+
+// ---------------------------------------------------------------- row-wise kernels (rows.cu)
+// y = LayerNorm(x (+ add_rows_mod)) * w + b.  x fp32 [M, D] (row stride ldx). Outputs (any may be null):
+//   out_f32 [M,D], out_bf16 [M,D], and out2 = y + post_add[row % post_mod] (bf16 and/or f32).
+struct LnArgs {
+  const float* x; int ldx;
+  const float* w; const float* b; float eps;
+  float* out_f32; bf16* out_bf16;
+  const float* post_add; int post_mod;   // optional positional term added after the norm
+  float* out2_f32; bf16* out2_bf16;
+  int M, D;
+};
+int layernorm_rows(const LnArgs& a, cudaStream_t stream);
+
+// fp32 (strided rows) -> bf16 contiguous [rows, cols]: row r = (r / inner) * outer_stride + (r % inner) * row_stride.
+int cast_rows_bf16(const float* src, long long outer_stride, long long row_stride, int inner, bf16* dst, int rows,
+                   int cols, cudaStream_t stream);
+
+// ---------------------------------------------------------------- encoder satellites (embed.cu)
+// video fp32 [B*T,3,H,W] -> patches bf16 [B*T*n, Kp] (k = c*p*p + i*p + j, zero padded to Kp).
+int im2col_patches(const float* video, bf16* out, int BT, int H, int W, int p, int Kp, cudaStream_t stream);
+// x[b, 0] = LN(cls + pos[0]); x[b, 1 + f*n + q] = LN(tok[(b*T+f)*n + q] + pos[1+q] + temporal[f]);  eps 1e-5
+int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, const float* temporal, const float* w,
+                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream);
+
+// ---------------------------------------------------------------- divided space-time attention (attn_*.cu)
+// qkv bf16 [B*N, 3*D] (q pre-scaled), N = 1 + T*n, heads of 64. out bf16 [B*N, D]; patch rows only.
+int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStream_t stream);
+int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStream_t stream);
+// CLS query row: attends all N keys (both attention kinds). Writes out[b*N + 0].
+int attn_cls(const bf16* qkv, bf16* out, int B, int N, int H, cudaStream_t stream);
+
+// ---------------------------------------------------------------- decoder satellites (decoder.cu)
+// Small-M fp32 linear: out[R,N] = act((in[R,K] (+ in_add[r % add_mod, K])) * W[N,K]^T + bias) (+ residual[R,N]).
+struct LinArgs {
+  const float* in; int ldi;
+  const float* in_add; int add_mod;       // optional, row-periodic (query_pos)
+  const float* W; const float* bias;      // W fp32 [N,K] row-major
+  const float* residual; int ldres;       // optional
+  float* out; int ldo;
+  int R, N, K;
+  int act;                                // 0 none, 1 relu, 2 sigmoid
+  int in_relu;                            // 1: apply ReLU to the input first (txt_proj = ReLU -> Linear)
+};
+int linear_f32(const LinArgs& a, cudaStream_t stream);
+// Query self-attention: q,k,v fp32 [B*Q, C] (q pre-scaled), heads of 64 -> out fp32 [B*Q, C].
+int self_attn_queries(const float* q, const float* k, const float* v, int ld, float* out, int B, int Q, int heads,
+                      cudaStream_t stream);
+// Query -> patch cross attention. q fp32 [B*Q, C] (pre-scaled); K,V bf16 rows [B*S] with row stride ldkv, head h at
+// column h*64.  Output fp32 [B*Q, C].  workspace: see cross_attn_workspace_bytes.
+size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S);
+int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
+               void* workspace, cudaStream_t stream);
+// boxes[l, b*T+t, q, :] head input: cond = hsproj[l,b,q,:] + frameterm[t,:]  (ObjDecoder frame_proj split)
+int add_frame_term(const float* hsproj, const float* frameterm, float* out, int LB, int T, int Q, int C,
+                   cudaStream_t stream);
+int f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream);
+// weight packing: dst bf16 [rows, cols_out] = src fp32 [rows, cols_in] (zero padded), first `scaled_rows` rows * scale
+int pack_weight_bf16(const float* src, bf16* dst, int rows, int cols_in, int cols_out, int scaled_rows, float scale,
+                     cudaStream_t stream);
+// dst[i] = src[i] * (i < scaled ? scale : 1)
+int scale_copy_f32(const float* src, float* dst, size_t n, size_t scaled, float scale, cudaStream_t stream);
+// dst[r, :cols] = src[r, col0 : col0+cols]  (src row stride lds)
+int slice_cols_f32(const float* src, int lds, int col0, float* dst, int rows, int cols, cudaStream_t stream);
+// pos[t*n + p, :] = pos_embed[1 + p, :] + temporal[t, :]   (both encoders' tiled position embedding)
+int build_pos3d(const float* pos_embed, const float* temporal, float* out, int T, int n, int C, cudaStream_t stream);
+// x / max(||x||, eps) per row
+int l2_normalize_rows(const float* x, float* out, int rows, int cols, float eps, cudaStream_t stream);
+int expand_logits(const float* src, float* dst, int LB, int rep, size_t per, cudaStream_t stream);
+
+// ---------------------------------------------------------------- scoring / boxes (score.cu, box.cu)
+int sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, cudaStream_t stream);
+// mode 0: argmax over columns -> int64 ; 1: row softmax(x*scale) ; 2: row log_softmax(x*scale)
+int row_reduce(const float* x, int rows, int cols, float scale, int mode, void* out, cudaStream_t stream);
+int box_cxcywh_to_xyxy(const float* in, float* out, long long nboxes, cudaStream_t stream);
+int box_xyxy_to_cxcywh(const float* in, float* out, long long nboxes, cudaStream_t stream);
+// pairwise on xyxy boxes: iou, union, giou (each [N,M], any may be null)
+int box_pairwise(const float* b1, const float* b2, int N, int M, float* iou, float* uni, float* giou,
+                 cudaStream_t stream);
+// matcher cost on cxcywh boxes: w_bbox * L1 + w_giou * (-GIoU)  -> [N,M]
+int box_match_cost(const float* pred, const float* tgt, int N, int M, float w_bbox, float w_giou, float* cost,
+                   cudaStream_t stream);
+
+}  // namespace hh

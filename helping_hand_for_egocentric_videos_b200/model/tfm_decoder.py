@@ -1,0 +1,239 @@
+"""Drop-in mirror of the reference's ``model/tfm_decoder.py`` (object-aware decoder) running on libhh_b200.so.
+
+``Cross_Attention`` / ``ObjDecoder`` keep the reference's constructor keywords, attributes (``.txt_proj``,
+``.obj_proj``, ``.transformer`` ...), ``state_dict`` keys and return values:
+
+    out, hs, attn, self_attn = model(video_grid)        # run/test_EgoMCQ.py:73 ; attn == self_attn == []
+
+The module tree holds parameters; ``ObjDecoder.forward`` (reference :183-233) is one C-ABI call (hh_decoder_forward)
+and the small projection heads are hh_linear_f32 calls.  Inference semantics: dropout (p=0.1 in the reference's
+training mode) is not applied and no autograd graph is recorded -- decoder training is SURVEY.md section 8f row 2.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from .LaviLa import _ParamSync
+
+
+class _NativeHead(nn.Sequential):
+    """nn.Sequential of Linear / ReLU layers (same child indices => same state_dict keys as the reference's
+    nn.Sequential heads, tfm_decoder.py:168-180) evaluated with hh_linear_f32, ReLUs fused into the linears."""
+
+    @torch.no_grad()
+    def forward(self, x):
+        mods = list(self)
+        pending_relu = False
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.ReLU):
+                pending_relu = True
+                i += 1
+                continue
+            assert isinstance(m, nn.Linear)
+            fuse_out = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            x = ops.linear_f32(x, m.weight.detach(), m.bias.detach() if m.bias is not None else None,
+                               act=1 if fuse_out else 0, in_relu=pending_relu)
+            pending_relu = False
+            i += 2 if fuse_out else 1
+        if pending_relu:
+            x = torch.relu(x)
+        return x
+
+
+class MLP(nn.Module):
+    """Parameter container for bbox_embed (reference :96-108)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu", normalize_before=False,
+                 sa_first=True):
+        super().__init__()
+        self.sa_first = sa_first
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, decoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(decoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+
+
+class Cross_Attention(nn.Module):
+    """Reference :50-93.  Only the configuration every reference script uses is implemented: pre-norm
+    (``normalize_before=True`` -- the post-norm branch of the reference cannot run),
+    ``return_intermediate_dec=True``, ReLU FFN, self-attention first."""
+
+    def __init__(self, d_model=512, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=2048,
+                 dropout=0.1, activation="relu", normalize_before=False, hidden_dim=768,
+                 return_intermediate_dec=False, sa_first=True):
+        super().__init__()
+        if not normalize_before or not return_intermediate_dec or activation != "relu" or not sa_first:
+            raise NotImplementedError("Cross_Attention (B200): normalize_before=True, return_intermediate_dec=True, "
+                                      "activation='relu', sa_first=True is the supported configuration")
+        self.pre_norm = nn.LayerNorm(d_model)
+        layer = TransformerDecoderLayer(d_model, nhead, dim_feedforward, dropout, activation, normalize_before,
+                                        sa_first=sa_first)
+        self.decoder = TransformerDecoder(layer, num_decoder_layers, nn.LayerNorm(d_model),
+                                          return_intermediate=return_intermediate_dec)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self.d_model = d_model
+        self.nhead = nhead
+        self.dec_layers = num_decoder_layers
+        self.enc_layers = num_encoder_layers
+        self.dim_feedforward = dim_feedforward
+        self.dropout_p = dropout
+
+
+class ObjDecoder(nn.Module):
+    """Reference :111-241."""
+
+    def __init__(self, transformer, num_classes, num_queries, feature_dim=768, aux_loss=False, pred_traj=True,
+                 num_frames=4, patches_per_frame=256, backbone='LaviLa', self_attn=False):
+        super().__init__()
+        if self_attn:
+            raise NotImplementedError("ObjDecoder(self_attn=True) is not used by any reference script")
+        if num_queries == 1:
+            raise NotImplementedError("the num_queries == 1 / n_decode = 10 branch (reference :135-137) is not implemented")
+        self.backbone = backbone
+        self.txt_proj = _NativeHead(nn.ReLU(), nn.Linear(768, 256))
+        self.vid_proj = _NativeHead(nn.Linear(768, 256))
+        self.num_queries = num_queries
+        self.transformer = transformer
+        hidden_dim = transformer.d_model
+        self.hidden_dim = hidden_dim
+        self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
+        self.bbox_embed = MLP(hidden_dim, hidden_dim, 4, 3)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.pred_traj = pred_traj
+        self.n_decode = 1
+        if self.pred_traj:
+            self.frame_index = nn.Embedding(num_frames, hidden_dim)
+            self.frame_proj = nn.Linear(hidden_dim * 2, hidden_dim)
+        self.aux_loss = aux_loss
+        self.pos_embed = nn.Parameter(torch.zeros(1, patches_per_frame + 1, hidden_dim))
+        self.temporal_embed = nn.Parameter(torch.zeros(1, num_frames, hidden_dim))
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        nn.init.trunc_normal_(self.temporal_embed, std=.02)
+        self.patches_per_frame = patches_per_frame
+        self.proj = nn.Linear(feature_dim, hidden_dim, bias=False)
+        self.num_frames = num_frames
+        self.obj_proj = _NativeHead(nn.Linear(hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, 256))
+        self._cfg = L.DecoderCfg(hidden_dim, transformer.nhead, transformer.dec_layers, transformer.dim_feedforward,
+                                 num_queries, num_classes + 1, feature_dim, num_frames, patches_per_frame,
+                                 1 if pred_traj else 0)
+        self._handle = None
+        self._sync = _ParamSync()
+        self._warned_train = False
+
+    # -- engine plumbing ---------------------------------------------------------------------------------------
+    def _engine(self):
+        if self._handle is None:
+            h = C.c_void_p()
+            L.check(L.load().hh_decoder_create(C.byref(h), C.byref(self._cfg)), "hh_decoder_create")
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and L._lib is not None:
+            L._lib.hh_decoder_destroy(h)
+            self._handle = None
+
+    def _engine_params(self):
+        skip = ("txt_proj.", "vid_proj.", "obj_proj.")
+        for k, p in self.named_parameters():
+            if not k.startswith(skip):
+                yield k, p
+
+    def sync_weights(self):
+        lib = L.load()
+        T = self.temporal_embed.shape[1]       # inflate_positional_embeds may have stretched it (run/test_epic.py:168-173)
+        if T != self._cfg.num_frames and not self.pred_traj:
+            if self._handle is not None:
+                lib.hh_decoder_destroy(self._handle)
+                self._handle = None
+            self._cfg.num_frames = T
+            self.num_frames = T
+            self._sync = _ParamSync()
+        h = self._engine()
+
+        def setter(key, src):
+            L.check(lib.hh_decoder_set_weight(h, key.encode(), L.ptr(src), src.numel(), L.stream_ptr()),
+                    "hh_decoder_set_weight(%s)" % key)
+        self._sync.sync(self._engine_params(), setter)
+
+    def flops_per_clip(self, T=None) -> float:
+        return L.load().hh_decoder_flops_per_clip(self._engine(), int(T or self.num_frames))
+
+    def last_launches(self) -> int:
+        return L.load().hh_decoder_last_launches(self._engine())
+
+    # -- reference API -----------------------------------------------------------------------------------------
+    def construct_3d_pos_embed(self, T):
+        tile_pos_embed = self.pos_embed[:, 1:, :].repeat(1, T, 1)
+        tile_temporal_embed = self.temporal_embed.repeat_interleave(self.patches_per_frame, 1)
+        return (tile_pos_embed + tile_temporal_embed).view(1, T, self.patches_per_frame, self.pos_embed.shape[-1])
+
+    @torch.no_grad()
+    def forward(self, features, use_checkpoint=False):
+        """features [B,T,n,F] (fp32, any strides with a unit innermost stride) -> (out, hs, [], [])."""
+        if not features.is_cuda:
+            raise RuntimeError("ObjDecoder (B200): input is on %s; there is no CPU fallback" % features.device)
+        if self.training and self.transformer.dropout_p > 0 and not self._warned_train:
+            warnings.warn("ObjDecoder (B200) runs the inference forward: dropout is not applied and no autograd graph "
+                          "is recorded (decoder training is not part of this build yet)")
+            self._warned_train = True
+        B, T, n, F = features.shape
+        if n != self.patches_per_frame or F != self._cfg.feature_dim:
+            raise RuntimeError("expected features [B,T,%d,%d], got %s" % (self.patches_per_frame, self._cfg.feature_dim,
+                                                                          tuple(features.shape)))
+        if features.dtype != torch.float32:
+            features = features.float()
+        if features.stride(3) != 1 or features.stride(1) != n * features.stride(2) or features.stride(2) % 4 \
+                or features.stride(0) % 4 or features.data_ptr() % 16:
+            features = features.contiguous()
+        self.sync_weights()
+        L_, Q, Cd, ncls = self._cfg.num_layers, self.num_queries, self.hidden_dim, self._cfg.num_classes1
+        traj = self.pred_traj and T == self.num_frames
+        dev = features.device
+        hs = torch.empty(L_, B, Q, Cd, dtype=torch.float32, device=dev)
+        logits = torch.empty(L_, B * (4 if traj else 1), Q, ncls, dtype=torch.float32, device=dev)
+        boxes = torch.empty(L_, B * (T if traj else 1), Q, 4, dtype=torch.float32, device=dev)
+        L.check(L.load().hh_decoder_forward(self._engine(), features.data_ptr(), features.stride(0), features.stride(2),
+                                            B, T, L.ptr(hs), L.ptr(logits), L.ptr(boxes), L.stream_ptr()),
+                "hh_decoder_forward")
+        out = {'pred_logits': logits[-1], 'pred_boxes': boxes[-1]}
+        if self.aux_loss:
+            out['aux_outputs'] = [{'pred_logits': a, 'pred_boxes': b} for a, b in zip(logits[:-1], boxes[:-1])]
+        return out, hs, [], []

@@ -1,0 +1,155 @@
+"""Tensor-level wrappers over the C ABI (one Python function per exported operator).
+
+PyTorch is used for device memory and streams only; every function enqueues hand-written sm_100a kernels on the
+current CUDA stream through libhh_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16, EPI_BIAS_RES_F32, EPI_BIAS_F32 = 0, 1, 2, 3
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return _c(t if t.dtype == torch.float32 else t.float())
+
+
+# ------------------------------------------------------------------------------------------ kernel-level
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, epilogue: int = EPI_BIAS_BF16,
+              residual: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """epilogue(a[M,K] @ w[N,K]^T): a, w bf16; bias fp32 [N]; residual fp32 [M,N] (may be `out`)."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    a, w = _c(a), _c(w)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    odt = torch.bfloat16 if epilogue in (EPI_BIAS_BF16, EPI_BIAS_QGELU_BF16) else torch.float32
+    if out is None:
+        out = torch.empty(M, N, dtype=odt, device=a.device)
+    assert out.dtype == odt and out.shape == (M, N) and out.is_contiguous()
+    L.check(L.load().hh_gemm_bf16(L.ptr(a), K, L.ptr(w), K, L.ptr(out), N, L.ptr(bias), L.ptr(residual),
+                                  N if residual is not None else 0, M, N, K, epilogue, L.stream_ptr()), "hh_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, want_f32=True, want_bf16=False):
+    x = _f32(x)
+    M, D = x.shape
+    o32 = torch.empty_like(x) if want_f32 else None
+    o16 = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    L.check(L.load().hh_layernorm(L.ptr(x), D, L.ptr(_f32(w)), L.ptr(_f32(b)), eps, L.ptr(o32), L.ptr(o16), M, D,
+                                  L.stream_ptr()), "hh_layernorm")
+    return o32, o16
+
+
+def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int) -> torch.Tensor:
+    """Divided space-time attention pieces on packed qkv (bf16 [B*(1+T*n), 3*H*64], q pre-scaled).
+    Returns dict of outputs for kind 'space', 'time' (patch rows) with the CLS row filled in both."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    N = 1 + T * n
+    outs = {}
+    lib = L.load()
+    for kind, name in ((0, "space"), (1, "time")):
+        o = torch.zeros(B * N, H * 64, dtype=torch.bfloat16, device=qkv.device)
+        L.check(lib.hh_attention(L.ptr(qkv), L.ptr(o), B, T, n, H, kind, L.stream_ptr()), "hh_attention")
+        L.check(lib.hh_attention(L.ptr(qkv), L.ptr(o), B, T, n, H, 2, L.stream_ptr()), "hh_attention(cls)")
+        outs[name] = o
+    return outs
+
+
+def cross_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, B: int, Q: int, heads: int, S: int) -> torch.Tensor:
+    """q fp32 [B*Q, heads*64] (pre-scaled); K, V bf16 [B*S, heads*64]."""
+    q = _f32(q)
+    assert K.dtype == torch.bfloat16 and V.dtype == torch.bfloat16 and K.is_contiguous() and V.is_contiguous()
+    out = torch.empty_like(q)
+    L.check(L.load().hh_cross_attention(L.ptr(q), L.ptr(K), L.ptr(V), K.shape[1], L.ptr(out), B, Q, heads, S,
+                                        L.stream_ptr()), "hh_cross_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ operators
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0,
+               in_relu: bool = False) -> torch.Tensor:
+    """nn.Linear on the last dim (fp32), optional input ReLU and output ReLU(1)/sigmoid(2)."""
+    shp = x.shape
+    x2 = _f32(x).reshape(-1, shp[-1])
+    N, K = weight.shape
+    out = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+    if x2.shape[0] > 0:
+        L.check(L.load().hh_linear_f32(L.ptr(x2), K, None, 0, L.ptr(_f32(weight)), L.ptr(_f32(bias)) if bias is not None else None,
+                                       None, 0, L.ptr(out), N, x2.shape[0], N, K, act, 1 if in_relu else 0,
+                                       L.stream_ptr()), "hh_linear_f32")
+    return out.reshape(*shp[:-1], N)
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    shp = x.shape
+    x2 = _f32(x).reshape(-1, shp[-1])
+    out = torch.empty_like(x2)
+    L.check(L.load().hh_l2_normalize(L.ptr(x2), L.ptr(out), x2.shape[0], x2.shape[1], eps, L.stream_ptr()),
+            "hh_l2_normalize")
+    return out.reshape(shp)
+
+
+def sim_matrix(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    a, b = _f32(a), _f32(b)
+    Na, d = a.shape
+    Nb = b.shape[0]
+    out = torch.empty(Na, Nb, dtype=torch.float32, device=a.device)
+    L.check(L.load().hh_sim_matrix(L.ptr(a), L.ptr(b), L.ptr(out), Na, Nb, d, eps, L.stream_ptr()), "hh_sim_matrix")
+    return out
+
+
+def row_argmax(x: torch.Tensor) -> torch.Tensor:
+    x = _f32(x)
+    out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    L.check(L.load().hh_row_reduce(L.ptr(x), x.shape[0], x.shape[1], 1.0, 0, L.ptr(out), L.stream_ptr()), "hh_row_reduce")
+    return out
+
+
+def row_softmax(x: torch.Tensor, scale: float = 1.0, log: bool = False) -> torch.Tensor:
+    x = _f32(x)
+    out = torch.empty_like(x)
+    L.check(L.load().hh_row_reduce(L.ptr(x), x.shape[0], x.shape[1], scale, 2 if log else 1, L.ptr(out),
+                                   L.stream_ptr()), "hh_row_reduce")
+    return out
+
+
+def box_convert(x: torch.Tensor, to_xyxy: bool) -> torch.Tensor:
+    shp = x.shape
+    assert shp[-1] == 4
+    x2 = _f32(x).reshape(-1, 4)
+    out = torch.empty_like(x2)
+    fn = L.load().hh_box_cxcywh_to_xyxy if to_xyxy else L.load().hh_box_xyxy_to_cxcywh
+    if x2.shape[0] > 0:
+        L.check(fn(L.ptr(x2), L.ptr(out), x2.shape[0], L.stream_ptr()), "hh_box_convert")
+    return out.reshape(shp)
+
+
+def box_pairwise(b1: torch.Tensor, b2: torch.Tensor):
+    """(iou, union, giou), each [N,M], for xyxy boxes."""
+    b1, b2 = _f32(b1), _f32(b2)
+    N, M = b1.shape[0], b2.shape[0]
+    iou = torch.empty(N, M, dtype=torch.float32, device=b1.device)
+    uni = torch.empty_like(iou)
+    giou = torch.empty_like(iou)
+    if N > 0 and M > 0:
+        L.check(L.load().hh_box_pairwise(L.ptr(b1), L.ptr(b2), N, M, L.ptr(iou), L.ptr(uni), L.ptr(giou), L.stream_ptr()),
+                "hh_box_pairwise")
+    return iou, uni, giou
+
+
+def box_match_cost(pred: torch.Tensor, tgt: torch.Tensor, w_bbox: float = 5.0, w_giou: float = 2.0) -> torch.Tensor:
+    pred, tgt = _f32(pred), _f32(tgt)
+    N, M = pred.shape[0], tgt.shape[0]
+    cost = torch.empty(N, M, dtype=torch.float32, device=pred.device)
+    if N > 0 and M > 0:
+        L.check(L.load().hh_box_match_cost(L.ptr(pred), L.ptr(tgt), N, M, w_bbox, w_giou, L.ptr(cost), L.stream_ptr()),
+                "hh_box_match_cost")
+    return cost

@@ -1,0 +1,153 @@
+/* libhh_b200.so -- C ABI of the B200-native Helping-Hands video-side forward path.
+ *
+ * The reference (Chuhanxx/helping_hand_for_egocentric_videos) has no FFI: its operator API for this path is the
+ * Python nn.Module boundary of model/LaviLa.py, model/tfm_decoder.py, model/metric.py and utils/box_ops.py.  The
+ * Python mirror of those modules (helping_hand_for_egocentric_videos_b200/model/*.py) binds exactly the entry points
+ * below through ctypes; each one names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer to a contiguous buffer owned by the caller, unless stated otherwise;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device;
+ *   - return value 0 = OK, negative = error (-1 bad handle, -2 bad argument, -3 CUDA failure);
+ *     hh_last_error() returns the message for the calling thread;
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute entry point fails with -3.
+ */
+#ifndef HH_B200_H_
+#define HH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hh_encoder hh_encoder;
+typedef struct hh_decoder hh_decoder;
+
+const char* hh_last_error(void);
+int hh_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Video encoder: SpaceTimeTransformer.forward_features  (model/LaviLa.py:537-573; blocks :345-390; attention :246-283)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int img_size;    /* 224 */
+  int patch_size;  /* 14 (L/14) or 16 (B/16) */
+  int num_frames;  /* T; forward requires exactly T frames (LaviLa.py:549-553) */
+  int embed_dim;   /* D: multiple of 128, <= 1024 */
+  int depth;       /* number of SpaceTimeBlocks */
+  int num_heads;   /* D / num_heads must be 64 */
+  int mlp_hidden;  /* 4 * D */
+} hh_encoder_cfg;
+
+int hh_encoder_create(hh_encoder** out, const hh_encoder_cfg* cfg);
+void hh_encoder_destroy(hh_encoder* enc);
+/* Copies one parameter (fp32, contiguous, `numel` elements) out of the caller's tensor.  `key` is the reference
+ * state_dict key relative to `visual.` (e.g. "blocks.3.timeattn.qkv.weight", "pos_embed", "ln_pre.bias";
+ * SURVEY.md section 8b).  Call again after the tensor changes (load_state_dict / .to() / inflate_positional_embeds). */
+int hh_encoder_set_weight(hh_encoder* enc, const char* key, const float* data, int64_t numel, void* stream);
+/* video fp32 [B,T,3,H,W] -> fmap fp32 [B, 1+T*n, D] (final norm applied to every token, LaviLa.py:573).
+ * x_cls of the reference is fmap[:,0,:] (LaviLa.py:570). */
+int hh_encoder_forward(hh_encoder* enc, const float* video, int B, float* fmap, void* stream);
+/* Test hook: fp32 residual stream after block `block` (0-based) of the last forward is not retained; instead run a
+ * truncated forward: blocks [0, nblocks) then the final norm. nblocks < 0 means all. */
+int hh_encoder_forward_n(hh_encoder* enc, const float* video, int B, int nblocks, float* fmap, void* stream);
+/* Algorithmic FLOPs of one clip through the encoder (SURVEY.md section 8d formula). */
+double hh_encoder_flops_per_clip(const hh_encoder* enc);
+/* Number of kernel launches issued by the last hh_encoder_forward call. */
+int hh_encoder_last_launches(const hh_encoder* enc);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Object-aware decoder: ObjDecoder.forward  (model/tfm_decoder.py:183-233) with Cross_Attention.forward (:76-93),
+ * TransformerDecoder.forward (:255-295) and TransformerDecoderLayer.forward_pre (:420-461), eval mode (no dropout).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int d_model;           /* C: 512 (multiple of 128, <= 1024; heads of 64) */
+  int nhead;             /* C / nhead must be 64 */
+  int num_layers;        /* 6 */
+  int dim_feedforward;   /* 2048 */
+  int num_queries;       /* Q = nq + 1 <= 16 */
+  int num_classes1;      /* num_classes + 1 = 22048 */
+  int feature_dim;       /* F: 1024 (L/14) or 768 (B/16) */
+  int num_frames;        /* T the position embedding was built for */
+  int patches_per_frame; /* n */
+  int pred_traj;         /* ObjDecoder(pred_traj=...) */
+} hh_decoder_cfg;
+
+int hh_decoder_create(hh_decoder** out, const hh_decoder_cfg* cfg);
+void hh_decoder_destroy(hh_decoder* dec);
+/* `key`: ObjDecoder state_dict key (e.g. "transformer.decoder.layers.0.multihead_attn.in_proj_weight"). */
+int hh_decoder_set_weight(hh_decoder* dec, const char* key, const float* data, int64_t numel, void* stream);
+/* features fp32 [B,T,n,F] given as a strided view: element (b,t,p,c) at features[b*stride_b + (t*n+p)*stride_row + c]
+ * (this is how run/test_EgoMCQ.py:69-70 slices image_feature_map[:,1:]).  Outputs (caller-allocated, fp32):
+ *   hs     [L, B, Q, C]
+ *   logits [L, B*rep, Q, num_classes1]   rep = 4 if pred_traj and T == num_frames (the reference's literal 4,
+ *                                        tfm_decoder.py:216) else 1
+ *   boxes  [L, B*Tb, Q, 4]               Tb = T if pred_traj and T == num_frames else 1
+ */
+int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
+                       float* hs, float* logits, float* boxes, void* stream);
+double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
+int hh_decoder_last_launches(const hh_decoder* dec);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stateless operators
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* sim_matrix(a, b) (model/metric.py:363-375): out[Na,Nb] = (a/max(|a|,eps)) . (b/max(|b|,eps))^T, fp32. */
+int hh_sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, void* stream);
+/* Row-wise reductions of scale*x [rows, cols]: mode 0 = argmax -> int64 out[rows] (EgoMCQ choice, metric.py:218);
+ * 1 = softmax, 2 = log_softmax -> fp32 out[rows, cols] (EgoNCE at scale 1/0.07, model/loss.py:61-69). */
+int hh_row_reduce(const float* x, int rows, int cols, float scale, int mode, void* out, void* stream);
+/* F.normalize(x, dim=-1) with eps (CLIP.forward, model/LaviLa.py:676-677). */
+int hh_l2_normalize(const float* x, float* out, int rows, int cols, float eps, void* stream);
+/* nn.Linear on fp32 rows: out = act(relu_in?(in (+ in_add[row % add_mod])) W^T + bias) (+ residual).
+ * W [N,K] row-major, K % 32 == 0.  act: 0 none, 1 ReLU, 2 sigmoid.  (ObjDecoder.obj_proj / txt_proj,
+ * tfm_decoder.py:168-180; CLIP image_projection, LaviLa.py:657.) */
+int hh_linear_f32(const float* in, int ldi, const float* in_add, int add_mod, const float* W, const float* bias,
+                  const float* residual, int ldres, float* out, int ldo, int R, int N, int K, int act, int in_relu,
+                  void* stream);
+/* utils/box_ops.py:9-13, :16-20 */
+int hh_box_cxcywh_to_xyxy(const float* in, float* out, int64_t nboxes, void* stream);
+int hh_box_xyxy_to_cxcywh(const float* in, float* out, int64_t nboxes, void* stream);
+/* box_iou + generalized_box_iou (utils/box_ops.py:24-61) on xyxy boxes; each output [N,M] may be NULL. */
+int hh_box_pairwise(const float* boxes1, const float* boxes2, int N, int M, float* iou, float* uni, float* giou,
+                    void* stream);
+/* HungarianMatcher cost with exclude_class (model/box_utils.py:75-88): w_bbox*L1 + w_giou*(-GIoU), cxcywh in. */
+int hh_box_match_cost(const float* pred, const float* tgt, int N, int M, float w_bbox, float w_giou, float* cost,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (used by the parity tests and the roofline bench; same kernels the engines launch)
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* C[M,N] = epilogue(A[M,K] W[N,K]^T): A, W bf16 (uint16 storage), K contiguous.  epilogue: 0 bias->bf16,
+ * 1 bias+QuickGELU->bf16, 2 bias+fp32 residual->fp32, 3 bias->fp32.  (nn.Linear calls of LaviLa.py:249,281,186,189) */
+int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
+                 const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream);
+/* LayerNorm rows (fp32 in): optional fp32 and bf16 outputs. */
+int hh_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, float* out_f32, void* out_bf16,
+                 int M, int D, void* stream);
+int hh_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Divided attention on packed qkv bf16 [B*(1+T*n), 3*H*64] with q pre-scaled -> out bf16 [B*(1+T*n), H*64].
+ * kind 0 = space, 1 = time (patch rows), 2 = CLS row. */
+int hh_attention(const void* qkv, void* out, int B, int T, int n, int H, int kind, void* stream);
+/* Query->patch cross attention (tfm_decoder.py:438-441 core): q fp32 [B*Q, heads*64] pre-scaled, K/V bf16 [B*S, ldkv]. */
+int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
+                       int S, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Data-parallel exchange: the one collective of the path (all-gather of embeddings for the cross-rank similarity
+ * matrix, run/train.py:36-37,126-128; _valid_all_gather, utils/train_utils.py:51-59).  NCCL is resolved at run time
+ * (dlopen of the libnccl.so.2 already loaded by the host framework); one communicator per process / GPU.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define HH_NCCL_ID_BYTES 128
+int hh_comm_unique_id(void* id_host);                                     /* rank 0: fills 128 host bytes */
+int hh_comm_create(void** comm, int nranks, int rank, const void* id_host); /* collective over all ranks */
+int hh_comm_destroy(void* comm);
+/* recv[r*bytes_per_rank ...] = rank r's send buffer, for every rank (ncclAllGather on `stream`). */
+int hh_allgather(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HH_B200_H_ */

@@ -1,0 +1,218 @@
+"""Kernel-level parity (GPU): every exported kernel entry point of libhh_b200.so against a plain PyTorch fp32
+statement of the same op (the floating-point counterpart of the oracle), through the C ABI.
+
+Tolerances: kernels that take bf16 operands are compared on the SAME bf16-rounded inputs, so what is left is the fp32
+accumulation order and the bf16 rounding of the output (rel 2^-8); fp32 kernels use 1e-5 relative; the box kernels are
+bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import hh_oracle as O  # noqa: E402
+
+
+def _ops():
+    from helping_hand_for_egocentric_videos_b200 import ops
+    return ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def _close(got, want, rtol, atol, name=""):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    lim = atol + rtol * want.abs()
+    bad = err > lim
+    assert not bad.any(), "%s: %d/%d out of tolerance, max err %.3e (ref scale %.3e)" % (
+        name, int(bad.sum()), bad.numel(), err.max().item(), want.abs().max().item())
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (300, 3072, 1024), (4097, 1024, 1024), (1000, 4096, 1024), (515, 1024, 4096),
+    (777, 768, 768), (260, 2304, 768), (1568, 1024, 640), (100, 22048, 512), (4100, 6144, 512), (65, 128, 128),
+    (129, 96, 72), (1, 8, 8),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_tcgen05(M, N, K, epi):
+    ops = _ops()
+    if epi in (0, 1) and N % 2:
+        pytest.skip("bf16 output needs even N")
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, seed=2, scale=1 / math.sqrt(K)).bfloat16()
+    bias = _rand(N, seed=3, scale=0.5)
+    res = _rand(M, N, seed=4) if epi == 2 else None
+    ref = a.float() @ w.float().t() + bias
+    if epi == 1:
+        ref = O.quick_gelu(ref)
+    if epi == 2:
+        ref = ref + res
+    got = ops.gemm_bf16(a, w, bias, epilogue=epi, residual=res)
+    if epi in (0, 1):
+        _close(got, ref, 2 ** -7, 2e-3, "gemm epi%d" % epi)
+    else:
+        _close(got, ref, 1e-4, 2e-4, "gemm epi%d" % epi)
+
+
+def test_gemm_no_bias_and_inplace_residual():
+    ops = _ops()
+    a = _rand(333, 256, seed=5).bfloat16()
+    w = _rand(512, 256, seed=6, scale=1 / 16).bfloat16()
+    x = _rand(333, 512, seed=7)
+    want = x + a.float() @ w.float().t()
+    got = ops.gemm_bf16(a, w, None, epilogue=2, residual=x, out=x)      # x <- x + a w^T, in place
+    assert got.data_ptr() == x.data_ptr()
+    _close(got, want, 1e-4, 2e-4, "in-place residual")
+
+
+def test_gemm_is_deterministic():
+    ops = _ops()
+    a = _rand(2000, 1024, seed=8).bfloat16()
+    w = _rand(1024, 1024, seed=9, scale=1 / 32).bfloat16()
+    r1 = ops.gemm_bf16(a, w, None, epilogue=3)
+    r2 = ops.gemm_bf16(a, w, None, epilogue=3)
+    assert torch.equal(r1, r2)
+
+
+def test_gemm_rejects_bad_arguments():
+    ops = _ops()
+    a = _rand(16, 12, seed=1).bfloat16()      # K = 12: not a multiple of 8
+    w = _rand(8, 12, seed=2).bfloat16()
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.gemm_bf16(a, w)
+
+
+@pytest.mark.parametrize("M,D", [(1, 128), (37, 512), (4097, 1024), (785, 768)])
+def test_layernorm(M, D):
+    ops = _ops()
+    x = _rand(M, D, seed=10, scale=3.0) + 0.7
+    w = 1 + 0.1 * _rand(D, seed=11)
+    b = 0.1 * _rand(D, seed=12)
+    for eps in (1e-5, 1e-6):
+        o32, o16 = ops.layernorm(x, w, b, eps, want_f32=True, want_bf16=True)
+        ref = F.layer_norm(x, (D,), w, b, eps)
+        _close(o32, ref, 1e-5, 1e-5, "ln f32")
+        _close(o16, ref, 2 ** -8, 1e-3, "ln bf16")
+
+
+def _ref_attention(qkv, B, T, n, H, mode):
+    """Masked dense attention on the packed (already bf16-rounded, q pre-scaled) qkv."""
+    N = 1 + T * n
+    D = H * 64
+    q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)
+    s = s.masked_fill(~O._group_mask(T, n, mode).to(s.device), float("-inf"))
+    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, D)
+
+
+@pytest.mark.parametrize("B,T,n,H", [(2, 3, 16, 2), (1, 4, 196, 12), (2, 16, 256, 2), (1, 4, 256, 16), (3, 1, 4, 1),
+                                     (1, 2, 50, 3), (1, 32, 16, 4), (1, 8, 64, 5)])
+def test_divided_attention(B, T, n, H):
+    ops = _ops()
+    N = 1 + T * n
+    qkv = _rand(B * N, 3 * H * 64, seed=20, scale=1.0)
+    qkv[:, :H * 64] *= 0.35            # plausible pre-scaled q magnitude
+    qkv = qkv.bfloat16()
+    outs = ops.attention(qkv, B, T, n, H)
+    for mode in ("space", "time"):
+        ref = _ref_attention(qkv, B, T, n, H, mode)
+        # P is rounded to bf16 before P.V in the tensor-core kernel: allow 2^-7 relative on O(1) outputs
+        _close(outs[mode], ref, 2 ** -6, 6e-3, "attention %s" % mode)
+
+
+@pytest.mark.parametrize("B,Q,heads,S", [(2, 5, 2, 48), (1, 13, 8, 4096), (3, 13, 8, 784), (2, 16, 1, 100), (1, 1, 2, 31)])
+def test_cross_attention(B, Q, heads, S):
+    ops = _ops()
+    C_ = heads * 64
+    q = _rand(B * Q, C_, seed=30, scale=0.3)
+    K = _rand(B * S, C_, seed=31).bfloat16()
+    V = _rand(B * S, C_, seed=32).bfloat16()
+    got = ops.cross_attention(q, K, V, B, Q, heads, S)
+    qh = q.view(B, Q, heads, 64).transpose(1, 2)
+    kh = K.float().view(B, S, heads, 64).transpose(1, 2)
+    vh = V.float().view(B, S, heads, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(B * Q, C_)
+    _close(got, ref, 1e-4, 2e-5, "cross attention")
+
+
+@pytest.mark.parametrize("R,N,K", [(13, 512, 512), (832, 2048, 512), (65, 4, 512), (7, 256, 768), (100, 100, 32)])
+def test_linear_f32(R, N, K):
+    ops = _ops()
+    x = _rand(R, K, seed=40)
+    w = _rand(N, K, seed=41, scale=1 / math.sqrt(K))
+    b = _rand(N, seed=42)
+    _close(ops.linear_f32(x, w, b), F.linear(x, w, b), 1e-5, 1e-5, "linear")
+    _close(ops.linear_f32(x, w, b, act=1), F.relu(F.linear(x, w, b)), 1e-5, 1e-5, "linear+relu")
+    _close(ops.linear_f32(x, w, b, act=2), torch.sigmoid(F.linear(x, w, b)), 1e-5, 1e-5, "linear+sigmoid")
+    _close(ops.linear_f32(x, w, None, in_relu=True), F.linear(F.relu(x), w), 1e-5, 1e-5, "relu+linear")
+
+
+def test_sim_matrix_and_reductions():
+    ops = _ops()
+    a = _rand(70, 256, seed=50)
+    b = _rand(133, 256, seed=51)
+    a[3] = 0                                # eps clamp (model/metric.py:368-370)
+    sim = ops.sim_matrix(a, b)
+    _close(sim, O.sim_matrix(a, b), 1e-5, 1e-6, "sim_matrix")
+    assert torch.equal(ops.row_argmax(sim), sim.argmax(-1))
+    _close(ops.row_softmax(sim, 1 / 0.07), torch.softmax(sim / 0.07, -1), 1e-4, 1e-7, "softmax")
+    _close(ops.row_softmax(sim, 1 / 0.07, log=True), torch.log_softmax(sim / 0.07, -1), 1e-5, 1e-5, "log_softmax")
+    ties = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0], [5.0, 5.0, 5.0, 5.0, 5.0]]).cuda()
+    assert ops.row_argmax(ties).tolist() == [1, 0]      # first maximum, like torch.argmax
+    _close(ops.l2_normalize(a), F.normalize(a, dim=-1), 1e-6, 1e-7, "l2_normalize")
+
+
+def test_sim_matrix_large_is_symmetric_and_unit_diagonal():
+    """Size-independent properties at the EPIC-MIR scale (BASELINE config 4): sim(a,a) is symmetric with a unit
+    diagonal, and every entry is a cosine."""
+    ops = _ops()
+    a = _rand(9728, 256, seed=52)
+    s = ops.sim_matrix(a, a)
+    assert (s.diagonal() - 1).abs().max() < 1e-5
+    assert (s - s.t()).abs().max() < 1e-6
+    assert s.abs().max() <= 1 + 1e-5
+
+
+def test_box_ops_bit_exact():
+    ops = _ops()
+    g = torch.Generator().manual_seed(60)
+    def rb(k):
+        return torch.cat([0.2 + 0.6 * torch.rand(k, 2, generator=g), 0.02 + 0.35 * torch.rand(k, 2, generator=g)], -1)
+    p, t = rb(2560), rb(512)
+    t[0] = p[3]
+    t[1, 2:] = 0
+    pc, tc = p.cuda(), t.cuda()
+    pxy = ops.box_convert(pc, True)
+    assert torch.equal(pxy.cpu(), O.box_cxcywh_to_xyxy(p))
+    assert torch.equal(ops.box_convert(pxy, False).cpu(), O.box_xyxy_to_cxcywh(O.box_cxcywh_to_xyxy(p)))
+    iou, uni, giou = ops.box_pairwise(pxy, ops.box_convert(tc, True))
+    riou, runi = O.box_iou(O.box_cxcywh_to_xyxy(p), O.box_cxcywh_to_xyxy(t))
+    rg = O.generalized_box_iou(O.box_cxcywh_to_xyxy(p), O.box_cxcywh_to_xyxy(t))
+    assert torch.equal(iou.cpu(), riou) and torch.equal(uni.cpu(), runi)
+    assert torch.equal(giou.cpu(), rg)
+    cost = ops.box_match_cost(pc, tc)
+    _close(cost, O.matcher_cost(p, t).cuda(), 1e-6, 1e-6, "matcher cost")   # cdist's summation order is unspecified
+    assert ops.box_convert(torch.empty(0, 4).cuda(), True).shape == (0, 4)   # empty input
+
+
+def test_hungarian_indices_from_gpu_cost_match_reference_cost():
+    """'box index outputs exact': scipy's assignment on our cost equals the assignment on the oracle's cost."""
+    from scipy.optimize import linear_sum_assignment
+    ops = _ops()
+    g = torch.Generator().manual_seed(61)
+    for trial in range(20):
+        nq, nt = 10, int(torch.randint(1, 5, (1,), generator=g))
+        p = torch.cat([0.2 + 0.6 * torch.rand(nq, 2, generator=g), 0.05 + 0.3 * torch.rand(nq, 2, generator=g)], -1)
+        t = torch.cat([0.2 + 0.6 * torch.rand(nt, 2, generator=g), 0.05 + 0.3 * torch.rand(nt, 2, generator=g)], -1)
+        mine = linear_sum_assignment(ops.box_match_cost(p.cuda(), t.cuda()).cpu().numpy())
+        ref = linear_sum_assignment(O.matcher_cost(p, t).numpy())
+        assert (mine[0] == ref[0]).all() and (mine[1] == ref[1]).all()

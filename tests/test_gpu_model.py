@@ -1,0 +1,204 @@
+"""Model-level parity (GPU): the drop-in modules (helping_hand_for_egocentric_videos_b200.model.*) against
+  (a) the committed golden fixtures produced by the UNMODIFIED reference (tests/golden/*.pt), and
+  (b) the oracle (oracle/hh_oracle.py, fp32 CPU) on identical seeded weights and inputs.
+
+Gates are the ones BASELINE.json states for the bf16 path vs the fp32 reference: embedding cosine >= 0.999,
+box L1 <= 1e-2, identical EgoMCQ argmax (checked where the fp32 margin exceeds the measured similarity error),
+exact box / noun indices."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import golden_cases as gc  # noqa: E402
+from oracle import hh_oracle as O  # noqa: E402
+
+
+def _mods():
+    from helping_hand_for_egocentric_videos_b200.model import LaviLa, tfm_decoder, metric
+    return LaviLa, tfm_decoder, metric
+
+
+def _cos(a, b):
+    return F.cosine_similarity(a.float().flatten(1), b.float().flatten(1), dim=1).min().item()
+
+
+def _build_backbone(case):
+    LaviLa, _, _ = _mods()
+    c = case["cfg"]
+    vis = LaviLa.SpaceTimeTransformer(img_size=c["img"], patch_size=c["patch"], embed_dim=c["D"], depth=c["L"],
+                                      num_heads=c["H"], num_frames=c["T"], time_init='zeros', ln_pre=True,
+                                      act_layer=LaviLa.QuickGELU)
+    vis.head = torch.nn.Identity()
+    clip = LaviLa.CLIP(embed_dim=256, vision_width=c["D"], vision_model=vis, context_length=77, vocab_size=c["vocab"],
+                       transformer_width=c["text_width"], transformer_heads=c["text_heads"],
+                       transformer_layers=c["text_layers"])
+    sd = gc.backbone_state_dict(case)
+    clip.load_state_dict(sd, strict=True)          # key/shape contract of SURVEY.md section 8b
+    return clip.cuda().eval(), sd
+
+
+def _build_decoder(case):
+    _, D, _ = _mods()
+    c = case["cfg"]
+    tr = D.Cross_Attention(d_model=c["C"], nhead=c["heads"], num_decoder_layers=c["layers"], dim_feedforward=c["ffn"],
+                           normalize_before=True, return_intermediate_dec=True)
+    dec = D.ObjDecoder(transformer=tr, num_classes=c["ncls"], num_queries=c["Q"], aux_loss=True, pred_traj=c["pred_traj"],
+                       feature_dim=c["F"], num_frames=c["T"], patches_per_frame=c["n"])
+    sd = gc.decoder_state_dict(case)
+    dec.load_state_dict(sd, strict=True)
+    return dec.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("name", ["enc_tiny", "enc_tiny_d1", "enc_c0"])
+def test_encoder_against_reference_golden(name):
+    case = gc.CASES[name]
+    ref = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
+    clip, _ = _build_backbone(case)
+    video, tokens = gc.make_inputs(case)
+    out = clip(video.cuda(), tokens.cuda(), return_feature_map=True)
+    got = gc.subsample(case, {k: out[k].cpu() for k in ref})
+    assert got["image_feature_map"].shape == ref["image_feature_map"].shape
+    assert _cos(got["image_embed"], ref["image_embed"]) >= 0.999
+    assert _cos(got["image_feature_map"], ref["image_feature_map"]) >= 0.999
+    err = (got["image_feature_map"] - ref["image_feature_map"]).abs().max().item()
+    assert err <= 0.15, err          # O(4) activations through up to 12 bf16 layers
+    # the text tower is plain fp32 PyTorch here: must agree tightly
+    assert torch.allclose(got["text_embed"], ref["text_embed"], atol=1e-4)
+
+
+def test_encoder_blocks_against_oracle():
+    """Per-depth parity: truncated forwards (1, 2 blocks) against the oracle's per-block activations."""
+    case = gc.CASES["enc_tiny"]
+    clip, sd = _build_backbone(case)
+    video, _ = gc.make_inputs(case)
+    c = case["cfg"]
+    with torch.no_grad():
+        _, _, blocks = O.encoder_forward(video, sd, c["H"], pfx="visual.", return_blocks=True)
+    for nb in (0, 1, 2):
+        _, fmap = clip.visual.forward_features(video.cuda(), _nblocks=nb)
+        x = O.encoder_embed(video, sd, "visual.") if nb == 0 else blocks[nb - 1]
+        want = F.layer_norm(x, (c["D"],), sd["visual.norm.weight"], sd["visual.norm.bias"], 1e-6)
+        err = (fmap.cpu() - want).abs().max().item()
+        assert err <= (2e-2 if nb == 0 else 6e-2), (nb, err)     # nb=0: bf16 patch-embed GEMM only
+        assert _cos(fmap.cpu(), want) >= 0.9995
+
+
+@pytest.mark.parametrize("name", ["dec_tiny_traj", "dec_tiny_notraj", "dec_c0"])
+def test_decoder_against_reference_golden(name):
+    case = gc.CASES[name]
+    ref = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
+    dec, _ = _build_decoder(case)
+    _, _, metric = _mods()
+    feats, text_feat = gc.make_inputs(case)
+    out, hs, a, b = dec(feats.cuda())
+    assert a == [] and b == []
+    vid = dec.obj_proj(hs[-1])[:, -1]
+    txt = dec.txt_proj(text_feat.cuda())
+    res = {"pred_logits": out["pred_logits"], "pred_boxes": out["pred_boxes"], "hs": hs,
+           "aux_boxes": torch.stack([x["pred_boxes"] for x in out["aux_outputs"]]),
+           "aux_logits0": out["aux_outputs"][0]["pred_logits"], "video_embed": vid, "text_embed": txt,
+           "sim": metric.sim_matrix(txt, vid)}
+    got = gc.subsample(case, {k: v.cpu() for k, v in res.items()})
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+    assert (got["pred_boxes"] - ref["pred_boxes"]).abs().max() <= 1e-2            # box L1 gate
+    assert (got["aux_boxes"] - ref["aux_boxes"]).abs().max() <= 1e-2
+    assert _cos(got["video_embed"], ref["video_embed"]) >= 0.999                  # embedding gate
+    assert _cos(got["hs"].flatten(0, 1), ref["hs"].flatten(0, 1)) >= 0.999
+    assert torch.allclose(got["text_embed"], ref["text_embed"], atol=1e-4)        # fp32 head
+    assert (got["sim"] - ref["sim"]).abs().max() <= 5e-3
+    assert (got["pred_logits"] - ref["pred_logits"]).abs().max() <= 5e-2
+    # class index parity where the reference's top-1 margin is above the logit error
+    top2 = ref["pred_logits"].topk(2, -1).values
+    sure = (top2[..., 0] - top2[..., 1]) > 0.1
+    assert torch.equal(got["pred_logits"].argmax(-1)[sure], ref["pred_logits"].argmax(-1)[sure])
+
+
+def test_decoder_accepts_the_strided_feature_map_view():
+    """run/test_EgoMCQ.py:69-70 hands the decoder a view of image_feature_map[:, 1:] -- no copy needed."""
+    case = gc.CASES["dec_tiny_traj"]
+    dec, _ = _build_decoder(case)
+    c = case["cfg"]
+    feats, _ = gc.make_inputs(case)
+    B = feats.shape[0]
+    fmap = torch.zeros(B, 1 + c["T"] * c["n"], c["F"]).cuda()
+    fmap[:, 1:] = feats.reshape(B, -1, c["F"]).cuda()
+    view = fmap[:, 1:].unflatten(1, (c["T"], c["n"]))
+    assert not view.is_contiguous()
+    o1, hs1, _, _ = dec(view)
+    o2, hs2, _, _ = dec(feats.cuda())
+    assert torch.equal(hs1, hs2) and torch.equal(o1["pred_boxes"], o2["pred_boxes"])
+
+
+def test_egomcq_end_to_end_choices():
+    """EgoMCQ-style scoring (run/test_EgoMCQ.py:56-79) on BASELINE config c0 geometry, reduced depth for CPU time:
+    G questions x 5 option clips + 1 caption; our choices vs the oracle's, margins logged."""
+    LaviLa, D, metric = _mods()
+    T, G = 4, 6
+    enc_case = dict(kind="encoder", seed=77, B=5 * G, G=G,
+                    cfg=dict(img=224, patch=16, D=768, L=2, H=12, T=T, text_width=768, text_heads=12, text_layers=1,
+                             vocab=128))
+    dec_case = dict(kind="decoder", seed=78, B=1, G=1,
+                    cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=5, n=196, T=T, F=768, ncls=99, pred_traj=True))
+    clip, bsd = _build_backbone(enc_case)
+    dec, dsd = _build_decoder(dec_case)
+    video, tokens = gc.make_inputs(enc_case)
+    sims, ref_sims = [], []
+    for g in range(G):
+        v, t = video[5 * g:5 * g + 5], tokens[g:g + 1]
+        out = clip(v.cuda(), t.cuda(), return_feature_map=True)
+        grid = out['image_feature_map'][:, 1:].unflatten(1, (T, 196))
+        txt = dec.txt_proj(out['text_feature_map'][0, t.argmax(-1).cuda()])
+        _, hs, _, _ = dec(grid)
+        vid = dec.obj_proj(hs[-1])[:, -1]
+        sims.append(metric.sim_matrix(txt, vid).cpu())
+        with torch.no_grad():
+            ro = O.clip_forward(v, t, bsd, heads=12, text_heads=12)
+            rgrid = ro['image_feature_map'][:, 1:].unflatten(1, (T, 196))
+            _, rhs, _, _ = O.decoder_forward(rgrid, dsd, heads=8, pred_traj=True)
+            ref_sims.append(O.sim_matrix(O.txt_proj(ro['text_feature_map'][0, t.argmax(-1)], dsd),
+                                         O.obj_proj(rhs[-1], dsd)[:, -1]))
+    sims, ref_sims = torch.stack(sims), torch.stack(ref_sims)          # [G,1,5]
+    err = (sims - ref_sims).abs().max().item()
+    top2 = ref_sims.reshape(G, 5).topk(2, -1).values
+    margin = top2[:, 0] - top2[:, 1]
+    mine = metric.egomcq_choices(sims.cuda()).cpu()
+    ref = O.egomcq_choices(ref_sims)
+    print("EgoMCQ sims max err %.2e ; margins %s ; choices %s vs %s" % (err, margin.tolist(), mine.tolist(), ref.tolist()))
+    assert err <= 5e-3
+    decided = margin > 2 * err
+    assert torch.equal(mine[decided], ref[decided])
+    labels = ref.clone()
+    types = torch.tensor([1, 2] * (G // 2))
+    acc = metric.egomcq_accuracy_metrics(sims, labels, types)
+    if bool(decided.all()):
+        assert acc == {"Intra-video": 100.0, "Inter-video": 100.0}
+
+
+def test_state_dict_roundtrip_and_resync():
+    """load_state_dict -> forward -> mutate a parameter in place -> forward sees the change (engine re-sync)."""
+    case = gc.CASES["enc_tiny_d1"]
+    clip, sd = _build_backbone(case)
+    video, _ = gc.make_inputs(case)
+    _, f1 = clip.visual.forward_features(video.cuda())
+    _, f1b = clip.visual.forward_features(video.cuda())
+    assert torch.equal(f1, f1b)
+    with torch.no_grad():
+        clip.visual.norm.weight.mul_(2.0)
+    _, f2 = clip.visual.forward_features(video.cuda())
+    w = sd["visual.norm.weight"].cuda()
+    b = sd["visual.norm.bias"].cuda()
+    assert torch.allclose((f1 - b) * 2 + b, f2, atol=1e-4)
+    assert set(clip.state_dict().keys()) == set(sd.keys())
+
+
+def test_cpu_input_fails_loudly():
+    case = gc.CASES["enc_tiny_d1"]
+    clip, _ = _build_backbone(case)
+    video, _ = gc.make_inputs(case)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        clip.visual.forward_features(video)
