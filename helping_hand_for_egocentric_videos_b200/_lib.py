@@ -43,6 +43,12 @@ SIGNATURES = {
     "hh_decoder_forward": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
     "hh_decoder_flops_per_clip": (C.c_double, [_p, _i]),
     "hh_decoder_last_launches": (_i, [_p]),
+    "hh_profile_num_classes": (_i, []),
+    "hh_profile_class_name": (C.c_char_p, [_i]),
+    "hh_encoder_set_profile": (_i, [_p, _i]),
+    "hh_encoder_profile": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i)]),
+    "hh_decoder_set_profile": (_i, [_p, _i]),
+    "hh_decoder_profile": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i)]),
     "hh_sim_matrix": (_i, [_p, _p, _p, _i, _i, _i, _f, _p]),
     "hh_row_reduce": (_i, [_p, _i, _i, _f, _i, _p, _p]),
     "hh_l2_normalize": (_i, [_p, _p, _i, _i, _f, _p]),

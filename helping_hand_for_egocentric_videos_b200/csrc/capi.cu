@@ -90,6 +90,35 @@ int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b,
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T) { return dec ? dec->impl.flops_per_clip(T) : 0.0; }
 int hh_decoder_last_launches(const hh_decoder* dec) { return dec ? dec->impl.launches : 0; }
 
+// ------------------------------------------------------------------------------------------ event profiler
+static const char* kClassNames[K_NUM] = {"gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_patch", "layernorm",
+                                         "attn_time", "attn_space", "attn_cls", "embed", "dec_memory_gemm",
+                                         "dec_cross_attn", "dec_query_side", "dec_heads"};
+int hh_profile_num_classes(void) { return K_NUM; }
+const char* hh_profile_class_name(int i) { return (i >= 0 && i < K_NUM) ? kClassNames[i] : ""; }
+int hh_encoder_set_profile(hh_encoder* enc, int on) {
+  if (!enc) return fail(-1, "hh_encoder_set_profile: null handle");
+  enc->impl.prof.enabled = on != 0;
+  return 0;
+}
+int hh_encoder_profile(hh_encoder* enc, double* ms, int* counts) {
+  HH_GUARD_BEGIN
+  if (!enc || !ms || !counts) return fail(-2, "hh_encoder_profile: null argument");
+  return enc->impl.prof.collect(ms, counts);
+  HH_GUARD_END
+}
+int hh_decoder_set_profile(hh_decoder* dec, int on) {
+  if (!dec) return fail(-1, "hh_decoder_set_profile: null handle");
+  dec->impl.prof.enabled = on != 0;
+  return 0;
+}
+int hh_decoder_profile(hh_decoder* dec, double* ms, int* counts) {
+  HH_GUARD_BEGIN
+  if (!dec || !ms || !counts) return fail(-2, "hh_decoder_profile: null argument");
+  return dec->impl.prof.collect(ms, counts);
+  HH_GUARD_END
+}
+
 // ------------------------------------------------------------------------------------------ stateless operators
 int hh_sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, void* stream) {
   return sim_matrix(a, b, out, Na, Nb, d, eps, S(stream));

@@ -326,6 +326,14 @@ expand_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int L
   }
 }
 
+__global__ void __launch_bounds__(256)
+expand_rows_scalar_kernel(const float* __restrict__ src, float* __restrict__ dst, int LB, int rep, size_t per) {
+  const size_t total = static_cast<size_t>(LB) * rep * per;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[(i / (per * rep)) * per + i % per];
+}
+
 }  // namespace
 
 int linear_f32(const LinArgs& a, cudaStream_t stream) {
@@ -378,12 +386,14 @@ int add_frame_term(const float* hsproj, const float* frameterm, float* out, int 
 }
 
 int expand_logits(const float* src, float* dst, int LB, int rep, size_t per, cudaStream_t stream) {
-  HH_REQUIRE(per % 4 == 0, "expand_logits: row size must be a multiple of 4 floats");
-  const size_t total = static_cast<size_t>(LB) * rep * (per / 4);
+  const bool vec = per % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  const size_t total = static_cast<size_t>(LB) * rep * (vec ? per / 4 : per);
   size_t blocks = (total + 255) / 256;
   const size_t cap = static_cast<size_t>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  expand_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, LB, rep, per / 4);
+  if (blocks < 1) blocks = 1;
+  if (vec) expand_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, LB, rep, per / 4);
+  else expand_rows_scalar_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, LB, rep, per);
   HH_CHECK_LAUNCH("expand_rows_kernel");
   return 0;
 }

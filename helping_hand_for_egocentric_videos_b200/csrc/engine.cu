@@ -76,6 +76,55 @@ int WeightStore::check_complete() const {
     if (_rc) return _rc;  \
   } while (0)
 
+// Launch `expr` bracketed by CUDA events of kernel class `cls` when profiling is on (hh_*_set_profile).
+#define PROF(cls, expr)       \
+  do {                        \
+    prof.begin(cls, s);       \
+    int _rc = (expr);         \
+    if (_rc) return _rc;      \
+    prof.end(s);              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ event profiler
+Profiler::~Profiler() {
+  for (cudaEvent_t e : pool) cudaEventDestroy(e);
+}
+void Profiler::begin(int cls, cudaStream_t s) {
+  if (!enabled) return;
+  if (used + 2 > pool.size()) {
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      pool.push_back(e);
+    }
+  }
+  recs.push_back({cls, used, used + 1});
+  cudaEventRecord(pool[used], s);
+  used += 2;
+  open = true;
+}
+void Profiler::end(cudaStream_t s) {
+  if (!enabled || !open) return;
+  cudaEventRecord(pool[recs.back().e1], s);
+  open = false;
+}
+int Profiler::collect(double* ms, int* counts) {
+  for (int i = 0; i < K_NUM; ++i) {
+    ms[i] = 0.0;
+    counts[i] = 0;
+  }
+  for (const Rec& r : recs) {
+    HH_CHECK_CUDA(cudaEventSynchronize(pool[r.e1]));
+    float t = 0.f;
+    HH_CHECK_CUDA(cudaEventElapsedTime(&t, pool[r.e0], pool[r.e1]));
+    ms[r.cls] += t;
+    counts[r.cls] += 1;
+  }
+  recs.clear();
+  used = 0;
+  return 0;
+}
+
 // ========================================================================================== encoder
 Encoder::Encoder(const hh_encoder_cfg& c) : cfg(c) {
   grid = cfg.img_size / cfg.patch_size;
@@ -183,11 +232,11 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
     const int P = Bc * T * n;
     const float* vid = video + static_cast<size_t>(b0) * T * frame_elems;
     // patch embed (LaviLa.py:218-223,540-542) + CLS/pos/temporal + ln_pre (:545-559)
-    RC(im2col_patches(vid, patches, Bc * T, cfg.img_size, cfg.img_size, cfg.patch_size, Kp, s));
-    RC(gemm_bf16(patches, Kp, static_cast<const bf16*>(w_patch.ptr), Kp, tok, D, nullptr, nullptr, 0, P, D, Kp,
-                 EPI_BIAS_F32, s));
-    RC(assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
-                          weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
+    PROF(K_EMBED, im2col_patches(vid, patches, Bc * T, cfg.img_size, cfg.img_size, cfg.patch_size, Kp, s));
+    PROF(K_GEMM_PATCH, gemm_bf16(patches, Kp, static_cast<const bf16*>(w_patch.ptr), Kp, tok, D, nullptr, nullptr, 0, P, D,
+                                 Kp, EPI_BIAS_F32, s));
+    PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
+                                     weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
     launches += 3;
     for (int i = 0; i < nblocks; ++i) {
       const std::string p = "blocks." + std::to_string(i) + ".";
@@ -204,15 +253,15 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
         ln.out_bf16 = a;
         ln.M = M;
         ln.D = D;
-        RC(layernorm_rows(ln, s));
-        RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
-                     static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
-        if (at == 0) RC(attn_time(qkv, a, Bc, T, n, H, s));
-        else RC(attn_space(qkv, a, Bc, T, n, H, s));
-        RC(attn_cls(qkv, a, Bc, N, H, s));
+        PROF(K_LN, layernorm_rows(ln, s));
+        PROF(K_GEMM_QKV, gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
+                                   static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
+        if (at == 0) PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, s));
+        else PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, s));
+        PROF(K_ATTN_CLS, attn_cls(qkv, a, Bc, N, H, s));
         // time: tr = x + proj(o)  (:364) ; space: x <- x + proj(o)  (:384, 'frozen-in-time': x, not tr)
-        RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, (at == 0) ? tr : x, D,
-                     weights.get(q + ".proj.bias"), x, D, M, D, D, EPI_BIAS_RES_F32, s));
+        PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, (at == 0) ? tr : x, D,
+                                    weights.get(q + ".proj.bias"), x, D, M, D, D, EPI_BIAS_RES_F32, s));
         launches += 5;
       }
       LnArgs ln{};
@@ -224,11 +273,11 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
       ln.out_bf16 = a;
       ln.M = M;
       ln.D = D;
-      RC(layernorm_rows(ln, s));
-      RC(gemm_bf16(a, D, static_cast<const bf16*>(L.w_fc1.ptr), D, h, Hd, weights.get(p + "mlp.fc1.bias"), nullptr, 0, M,
-                   Hd, D, EPI_BIAS_QGELU_BF16, s));
-      RC(gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, x, D, weights.get(p + "mlp.fc2.bias"), x, D, M, D,
-                   Hd, EPI_BIAS_RES_F32, s));
+      PROF(K_LN, layernorm_rows(ln, s));
+      PROF(K_GEMM_FC1, gemm_bf16(a, D, static_cast<const bf16*>(L.w_fc1.ptr), D, h, Hd, weights.get(p + "mlp.fc1.bias"), nullptr,
+                                 0, M, Hd, D, EPI_BIAS_QGELU_BF16, s));
+      PROF(K_GEMM_FC2, gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, x, D, weights.get(p + "mlp.fc2.bias"), x, D, M,
+                                 D, Hd, EPI_BIAS_RES_F32, s));
       launches += 3;
     }
     LnArgs ln{};
@@ -240,7 +289,7 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
     ln.out_f32 = fmap + static_cast<size_t>(b0) * N * D;
     ln.M = M;
     ln.D = D;
-    RC(layernorm_rows(ln, s));
+    PROF(K_LN, layernorm_rows(ln, s));
     launches += 1;
   }
   return 0;
@@ -250,7 +299,7 @@ double Encoder::flops_per_clip() const {
   // F_enc = 2 nT 3p^2 D + L [32 N D^2 + 4 D (n T (T+1) + N) + 4 D (T n (n+1) + N)] + 2 D 256
   const double D = cfg.embed_dim, T = cfg.num_frames, nn = n, NN = N, L = cfg.depth;
   const double ratio = static_cast<double>(cfg.mlp_hidden) / cfg.embed_dim;
-  const double lin = (8.0 + 4.0 * ratio) * NN * D * D;  // qkv x2 (12) + proj x2 (4) + mlp (4*ratio), x2 flops -> 32 at ratio 4
+  const double lin = (16.0 + 4.0 * ratio) * NN * D * D;  // qkv x2 (12) + proj x2 (4) + mlp (4*ratio) -> 32 at ratio 4
   return 2.0 * nn * T * Kpatch * D + L * (lin + 4.0 * D * (nn * T * (T + 1) + NN) + 4.0 * D * (T * nn * (nn + 1) + NN)) +
          2.0 * D * 256.0;
 }
@@ -303,7 +352,7 @@ int Decoder::validate(const hh_decoder_cfg& c) {
   HH_REQUIRE(c.nhead > 0 && c.d_model == c.nhead * 64, "decoder: head dim must be 64");
   HH_REQUIRE(c.num_queries >= 1 && c.num_queries <= 16, "decoder: 1..16 queries (num_queries==1 n_decode path unsupported)");
   HH_REQUIRE(c.num_layers >= 1 && c.dim_feedforward % 32 == 0, "decoder: layers / ffn");
-  HH_REQUIRE(c.feature_dim % 8 == 0 && c.num_classes1 % 4 == 0, "decoder: feature_dim % 8, (num_classes+1) % 4");
+  HH_REQUIRE(c.feature_dim % 8 == 0 && c.num_classes1 >= 1, "decoder: feature_dim must be a multiple of 8");
   HH_REQUIRE(c.num_frames >= 1 && c.patches_per_frame >= 1, "decoder: frames / patches");
   return 0;
 }
@@ -416,8 +465,8 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   const float* qpos = weights.get("query_embed.weight");
 
   // proj (no bias, :200) -> pre_norm (:86) ; memory and memory+pos in bf16 for the K/V GEMMs
-  RC(cast_rows_bf16(features, stride_b, stride_row, S, feat, static_cast<int>(BS), F, s));
-  RC(gemm_bf16(feat, F, static_cast<const bf16*>(w_proj.ptr), F, memf, C, nullptr, nullptr, 0, static_cast<int>(BS), C, F,
+  PROF(K_DEC_GEMM, cast_rows_bf16(features, stride_b, stride_row, S, feat, static_cast<int>(BS), F, s));
+  PROF(K_DEC_GEMM, gemm_bf16(feat, F, static_cast<const bf16*>(w_proj.ptr), F, memf, C, nullptr, nullptr, 0, static_cast<int>(BS), C, F,
                EPI_BIAS_F32, s));
   LnArgs ln{};
   ln.x = memf; ln.ldx = C;
@@ -425,10 +474,10 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   ln.out_bf16 = mem;
   ln.post_add = static_cast<const float*>(pos3d.ptr); ln.post_mod = S; ln.out2_bf16 = mempos;
   ln.M = static_cast<int>(BS); ln.D = C;
-  RC(layernorm_rows(ln, s));
-  RC(gemm_bf16(mempos, C, static_cast<const bf16*>(w_kall.ptr), C, Kall, Lr * C, static_cast<const float*>(b_kall.ptr),
+  PROF(K_DEC_GEMM, layernorm_rows(ln, s));
+  PROF(K_DEC_GEMM, gemm_bf16(mempos, C, static_cast<const bf16*>(w_kall.ptr), C, Kall, Lr * C, static_cast<const float*>(b_kall.ptr),
                nullptr, 0, static_cast<int>(BS), Lr * C, C, EPI_BIAS_BF16, s));
-  RC(gemm_bf16(mem, C, static_cast<const bf16*>(w_vall.ptr), C, Vall, Lr * C, static_cast<const float*>(b_vall.ptr), nullptr,
+  PROF(K_DEC_GEMM, gemm_bf16(mem, C, static_cast<const bf16*>(w_vall.ptr), C, Vall, Lr * C, static_cast<const float*>(b_vall.ptr), nullptr,
                0, static_cast<int>(BS), Lr * C, C, EPI_BIAS_BF16, s));
   HH_CHECK_CUDA(cudaMemsetAsync(tgt, 0, static_cast<size_t>(R) * C * 4, s));  // tgt = zeros (:84)
   launches += 6;
@@ -444,28 +493,28 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
     const float* wsa = static_cast<const float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C;
     const float* bsa = static_cast<const float*>(b_sa.ptr) + static_cast<size_t>(i) * 3 * C;
     // self attention over the queries (:431-435)
-    RC(lnq(tgt, p + "norm1", t2));
-    RC(lin(t2, C, qpos, Q, wsa, bsa, nullptr, 0, qkv, 3 * C, R, 2 * C, C, 0, s));                       // q,k <- t2+qpos
-    RC(lin(t2, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, qkv + 2 * C, 3 * C, R, C, C, 0, s));
-    RC(self_attn_queries(qkv, qkv + C, qkv + 2 * C, 3 * C, o, B, Q, heads, s));
-    RC(lin(o, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), tgt, C,
+    PROF(K_DEC_QUERY, lnq(tgt, p + "norm1", t2));
+    PROF(K_DEC_QUERY, lin(t2, C, qpos, Q, wsa, bsa, nullptr, 0, qkv, 3 * C, R, 2 * C, C, 0, s));                       // q,k <- t2+qpos
+    PROF(K_DEC_QUERY, lin(t2, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, qkv + 2 * C, 3 * C, R, C, C, 0, s));
+    PROF(K_DEC_QUERY, self_attn_queries(qkv, qkv + C, qkv + 2 * C, 3 * C, o, B, Q, heads, s));
+    PROF(K_DEC_QUERY, lin(o, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), tgt, C,
            tgt, C, R, C, C, 0, s));
     // cross attention to the patch tokens (:436-441,456)
-    RC(lnq(tgt, p + "norm2", t2));
-    RC(lin(t2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
+    PROF(K_DEC_QUERY, lnq(tgt, p + "norm2", t2));
+    PROF(K_DEC_QUERY, lin(t2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
            static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, qkv, C, R, C, C, 0, s));
-    RC(cross_attn(qkv, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, o, B, Q, heads, S,
+    PROF(K_DEC_CROSS, cross_attn(qkv, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, o, B, Q, heads, S,
                   ws_cross.ptr, s));
-    RC(lin(o, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
+    PROF(K_DEC_QUERY, lin(o, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
            tgt, C, tgt, C, R, C, C, 0, s));
     // FFN (:457-459)
-    RC(lnq(tgt, p + "norm3", t2));
-    RC(lin(t2, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, ffn, Fd, R, Fd, C,
+    PROF(K_DEC_QUERY, lnq(tgt, p + "norm3", t2));
+    PROF(K_DEC_QUERY, lin(t2, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, ffn, Fd, R, Fd, C,
            1, s));
-    RC(lin(ffn, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), tgt, C, tgt, C, R, C, Fd, 0,
+    PROF(K_DEC_QUERY, lin(ffn, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), tgt, C, tgt, C, R, C, Fd, 0,
            s));
     // intermediate output through the shared final norm (:282,287-291)
-    RC(lnq(tgt, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
+    PROF(K_DEC_QUERY, lnq(tgt, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
     launches += 15;
   }
 
@@ -484,24 +533,24 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   hp += rows_box * C * 4;
   float* logits_raw = traj ? reinterpret_cast<float*>(hp) : logits;
 
-  RC(f32_to_bf16(hs, hs16, LR * C, s));
-  RC(gemm_bf16(hs16, C, static_cast<const bf16*>(w_cls.ptr), C, logits_raw, ncls, weights.get("class_embed.bias"), nullptr, 0,
+  PROF(K_DEC_HEADS, f32_to_bf16(hs, hs16, LR * C, s));
+  PROF(K_DEC_HEADS, gemm_bf16(hs16, C, static_cast<const bf16*>(w_cls.ptr), C, logits_raw, ncls, weights.get("class_embed.bias"), nullptr, 0,
                static_cast<int>(LR), ncls, C, EPI_BIAS_F32, s));  // class_embed (:208)
   launches += 2;
   const float* box_in = hs;
   if (traj) {
-    RC(expand_logits(logits_raw, logits, Lr * B, 4, static_cast<size_t>(Q) * ncls, s));  // literal 4 (:216)
-    RC(lin(hs, C, nullptr, 0, static_cast<const float*>(w_f1.ptr), nullptr, nullptr, 0, hsproj, C, static_cast<int>(LR), C, C, 0, s));
-    RC(add_frame_term(hsproj, static_cast<const float*>(frameterm.ptr), cond, Lr * B, T, Q, C, s));
+    PROF(K_DEC_HEADS, expand_logits(logits_raw, logits, Lr * B, 4, static_cast<size_t>(Q) * ncls, s));  // literal 4 (:216)
+    PROF(K_DEC_HEADS, lin(hs, C, nullptr, 0, static_cast<const float*>(w_f1.ptr), nullptr, nullptr, 0, hsproj, C, static_cast<int>(LR), C, C, 0, s));
+    PROF(K_DEC_HEADS, add_frame_term(hsproj, static_cast<const float*>(frameterm.ptr), cond, Lr * B, T, Q, C, s));
     box_in = cond;
     launches += 3;
   }
   // bbox_embed: 3-layer MLP + sigmoid (:228)
-  RC(lin(box_in, C, nullptr, 0, weights.get("bbox_embed.layers.0.weight"), weights.get("bbox_embed.layers.0.bias"), nullptr, 0, x1,
+  PROF(K_DEC_HEADS, lin(box_in, C, nullptr, 0, weights.get("bbox_embed.layers.0.weight"), weights.get("bbox_embed.layers.0.bias"), nullptr, 0, x1,
          C, static_cast<int>(rows_box), C, C, 1, s));
-  RC(lin(x1, C, nullptr, 0, weights.get("bbox_embed.layers.1.weight"), weights.get("bbox_embed.layers.1.bias"), nullptr, 0, x2, C,
+  PROF(K_DEC_HEADS, lin(x1, C, nullptr, 0, weights.get("bbox_embed.layers.1.weight"), weights.get("bbox_embed.layers.1.bias"), nullptr, 0, x2, C,
          static_cast<int>(rows_box), C, C, 1, s));
-  RC(lin(x2, C, nullptr, 0, weights.get("bbox_embed.layers.2.weight"), weights.get("bbox_embed.layers.2.bias"), nullptr, 0, boxes,
+  PROF(K_DEC_HEADS, lin(x2, C, nullptr, 0, weights.get("bbox_embed.layers.2.weight"), weights.get("bbox_embed.layers.2.bias"), nullptr, 0, boxes,
          4, static_cast<int>(rows_box), 4, C, 2, s));
   launches += 3;
   return 0;

@@ -31,7 +31,27 @@ struct WeightStore {
   int check_complete() const;
 };
 
+// Kernel classes reported by the event profiler (hh_encoder_profile / hh_decoder_profile).
+enum KernelClass {
+  K_GEMM_QKV = 0, K_GEMM_PROJ, K_GEMM_FC1, K_GEMM_FC2, K_GEMM_PATCH, K_LN, K_ATTN_TIME, K_ATTN_SPACE, K_ATTN_CLS,
+  K_EMBED, K_DEC_GEMM, K_DEC_CROSS, K_DEC_QUERY, K_DEC_HEADS, K_NUM
+};
+
+struct Profiler {
+  bool enabled = false;
+  bool open = false;
+  struct Rec { int cls; size_t e0, e1; };
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<Rec> recs;
+  ~Profiler();
+  void begin(int cls, cudaStream_t s);
+  void end(cudaStream_t s);
+  int collect(double* ms, int* counts);  // waits for the recorded events; sums per class; resets
+};
+
 struct Encoder {
+  Profiler prof;
   hh_encoder_cfg cfg;
   int grid, n, N, Kpatch, Kp;
   int max_chunk = 64;  // clips per pass through the workspace
@@ -53,6 +73,7 @@ struct Encoder {
 };
 
 struct Decoder {
+  Profiler prof;
   hh_decoder_cfg cfg;
   int launches = 0;
   WeightStore weights;

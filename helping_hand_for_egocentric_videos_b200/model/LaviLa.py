@@ -185,6 +185,18 @@ class SpaceTimeTransformer(nn.Module):
     def last_launches(self) -> int:
         return L.load().hh_encoder_last_launches(self._engine())
 
+    def set_profile(self, on: bool):
+        """Record CUDA events around every kernel launch of the engine (see profile())."""
+        L.check(L.load().hh_encoder_set_profile(self._engine(), 1 if on else 0), "hh_encoder_set_profile")
+
+    def profile(self):
+        """{kernel class: (milliseconds, launches)} since the last call; waits for the recorded events."""
+        lib = L.load()
+        k = lib.hh_profile_num_classes()
+        ms, cnt = (C.c_double * k)(), (C.c_int * k)()
+        L.check(lib.hh_encoder_profile(self._engine(), ms, cnt), "hh_encoder_profile")
+        return {lib.hh_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(k) if cnt[i]}
+
     # -- reference API -----------------------------------------------------------------------------------------
     @torch.jit.ignore
     def no_weight_decay(self):

@@ -91,6 +91,16 @@ int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b,
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
 int hh_decoder_last_launches(const hh_decoder* dec);
 
+/* Per-kernel-class device timing (CUDA events recorded on the launching stream around every launch while enabled).
+ * hh_*_profile waits for the recorded events, writes the summed milliseconds and launch counts of every class
+ * (arrays of hh_profile_num_classes() entries) since the previous call, and resets the recorder. */
+int hh_profile_num_classes(void);
+const char* hh_profile_class_name(int cls);
+int hh_encoder_set_profile(hh_encoder* enc, int on);
+int hh_encoder_profile(hh_encoder* enc, double* ms, int* counts);
+int hh_decoder_set_profile(hh_decoder* dec, int on);
+int hh_decoder_profile(hh_decoder* dec, double* ms, int* counts);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Stateless operators
  * ---------------------------------------------------------------------------------------------------------------- */

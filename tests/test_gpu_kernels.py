@@ -87,7 +87,7 @@ def test_gemm_rejects_bad_arguments():
     ops = _ops()
     a = _rand(16, 12, seed=1).bfloat16()      # K = 12: not a multiple of 8
     w = _rand(8, 12, seed=2).bfloat16()
-    with pytest.raises(RuntimeError, match="multiple of 8"):
+    with pytest.raises(RuntimeError, match="multiples of 8"):
         ops.gemm_bf16(a, w)
 
 
