@@ -213,14 +213,14 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
   RC(ws_patches.reserve(Pc * Kp * 2));
   RC(ws_tok.reserve(Pc * D * 4));
   RC(ws_x.reserve(Mc * D * 4));
-  RC(ws_tr.reserve(Mc * D * 4));
+  RC(ws_dl.reserve(Mc * D * 2));
   RC(ws_a.reserve(Mc * D * 2));
   RC(ws_qkv.reserve(Mc * 3 * D * 2));
   RC(ws_h.reserve(Mc * Hd * 2));
   bf16* patches = static_cast<bf16*>(ws_patches.ptr);
   float* tok = static_cast<float*>(ws_tok.ptr);
   float* x = static_cast<float*>(ws_x.ptr);
-  float* tr = static_cast<float*>(ws_tr.ptr);
+  bf16* dl = static_cast<bf16*>(ws_dl.ptr);
   bf16* a = static_cast<bf16*>(ws_a.ptr);
   bf16* qkv = static_cast<bf16*>(ws_qkv.ptr);
   bf16* h = static_cast<bf16*>(ws_h.ptr);
@@ -238,58 +238,53 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
     PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
                                      weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
     launches += 3;
+    const bf16* pending = nullptr;  // bf16 branch output not yet folded into the fp32 residual stream x
+    auto ln_fused = [&](const bf16* delta, bool write_x, const std::string& nm, float eps, bf16* out16, float* out32) {
+      LnArgs ln{};
+      ln.x = x;
+      ln.ldx = D;
+      ln.delta = delta;
+      ln.xsum_out = (delta && write_x) ? x : nullptr;
+      ln.w = weights.get(nm + ".weight");
+      ln.b = weights.get(nm + ".bias");
+      ln.eps = eps;
+      ln.out_bf16 = out16;
+      ln.out_f32 = out32;
+      ln.M = M;
+      ln.D = D;
+      prof.begin(K_LN, s);
+      int rc = layernorm_rows(ln, s);
+      prof.end(s);
+      return rc;
+    };
     for (int i = 0; i < nblocks; ++i) {
       const std::string p = "blocks." + std::to_string(i) + ".";
       const Layer& L = layers[i];
-      for (int at = 0; at < 2; ++at) {  // 0 = time (norm3 on x), 1 = space (norm1 on x + time_out)
-        const std::string nm = p + (at == 0 ? "norm3" : "norm1");
+      // Residual adds are folded into the LayerNorm that follows them (one fp32 pass instead of a GEMM-epilogue
+      // read-modify-write):  norm3 reads x + mlp_out(prev) and stores it as the new x;  norm1 reads x + time_out
+      // (never stored: 'frozen-in-time' discards it, LaviLa.py:364,384);  norm2 reads x + space_out and stores it.
+      for (int at = 0; at < 2; ++at) {  // 0 = time (norm3), 1 = space (norm1)
         const std::string q = p + (at == 0 ? "timeattn" : "attn");
-        LnArgs ln{};
-        ln.x = (at == 0) ? x : tr;
-        ln.ldx = D;
-        ln.w = weights.get(nm + ".weight");
-        ln.b = weights.get(nm + ".bias");
-        ln.eps = 1e-6f;
-        ln.out_bf16 = a;
-        ln.M = M;
-        ln.D = D;
-        PROF(K_LN, layernorm_rows(ln, s));
+        if (at == 0) RC(ln_fused(pending, true, p + "norm3", 1e-6f, a, nullptr));
+        else RC(ln_fused(dl, false, p + "norm1", 1e-6f, a, nullptr));
         PROF(K_GEMM_QKV, gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
                                    static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
         if (at == 0) PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, s));
         else PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, s));
         PROF(K_ATTN_CLS, attn_cls(qkv, a, Bc, N, H, s));
-        // time: tr = x + proj(o)  (:364) ; space: x <- x + proj(o)  (:384, 'frozen-in-time': x, not tr)
-        PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, (at == 0) ? tr : x, D,
-                                    weights.get(q + ".proj.bias"), x, D, M, D, D, EPI_BIAS_RES_F32, s));
+        PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, dl, D,
+                                    weights.get(q + ".proj.bias"), nullptr, 0, M, D, D, EPI_BIAS_BF16, s));
         launches += 5;
       }
-      LnArgs ln{};
-      ln.x = x;
-      ln.ldx = D;
-      ln.w = weights.get(p + "norm2.weight");
-      ln.b = weights.get(p + "norm2.bias");
-      ln.eps = 1e-6f;
-      ln.out_bf16 = a;
-      ln.M = M;
-      ln.D = D;
-      PROF(K_LN, layernorm_rows(ln, s));
+      RC(ln_fused(dl, true, p + "norm2", 1e-6f, a, nullptr));  // x <- x + space_out ; a = norm2(x)
       PROF(K_GEMM_FC1, gemm_bf16(a, D, static_cast<const bf16*>(L.w_fc1.ptr), D, h, Hd, weights.get(p + "mlp.fc1.bias"), nullptr,
                                  0, M, Hd, D, EPI_BIAS_QGELU_BF16, s));
-      PROF(K_GEMM_FC2, gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, x, D, weights.get(p + "mlp.fc2.bias"), x, D, M,
-                                 D, Hd, EPI_BIAS_RES_F32, s));
+      PROF(K_GEMM_FC2, gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, dl, D, weights.get(p + "mlp.fc2.bias"), nullptr,
+                                 0, M, D, Hd, EPI_BIAS_BF16, s));
+      pending = dl;  // x + mlp_out is formed by the next norm3 (or the final norm)
       launches += 3;
     }
-    LnArgs ln{};
-    ln.x = x;
-    ln.ldx = D;
-    ln.w = weights.get("norm.weight");
-    ln.b = weights.get("norm.bias");
-    ln.eps = 1e-6f;
-    ln.out_f32 = fmap + static_cast<size_t>(b0) * N * D;
-    ln.M = M;
-    ln.D = D;
-    PROF(K_LN, layernorm_rows(ln, s));
+    RC(ln_fused(pending, false, "norm", 1e-6f, nullptr, fmap + static_cast<size_t>(b0) * N * D));
     launches += 1;
   }
   return 0;

@@ -35,7 +35,8 @@ struct Cfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int EPI_BYTES = 4 * 32 * STAGE_LD * 4;
+  static constexpr int EPI_SLOTS = 2;                              // per-warp ring of 32-row x 128-byte store slots
+  static constexpr int EPI_BYTES = 4 * EPI_SLOTS * 4096;            // (>= the 4 x 32 x 33 words of the direct path)
   static constexpr int BIAS_BYTES = BLOCK_N * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
@@ -52,13 +53,24 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)   (model/openai_model.py:177-179)
-  return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  // x * sigmoid(1.702 x) (model/openai_model.py:177-179) = 0.5 x (1 + tanh(0.851 x)): one MUFU op per element
+  // (tanh.approx.f32, rel. error 2^-11, below the bf16 rounding of the output) instead of ex2 + rcp.
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
-template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// TMA_STORE: the epilogue writes 32-row x 128-byte boxes through shared memory with cp.async.bulk.tensor stores
+// (needs a 16-byte aligned output with a 16-byte multiple row pitch); otherwise rows are stored directly.
+template <int BLOCK_N, int EPI, bool TMA_STORE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_c, const GemmArgs p) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,6 +93,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if constexpr (TMA_STORE) tma_prefetch_desc(&tma_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -169,6 +182,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..127
     int acc = 0;
     uint32_t acc_phase = 0;
+    int epi_slot = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n;
       const int n_blk = tile - m_blk * p.tiles_n;
@@ -186,7 +200,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
-      if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
+      if constexpr (TMA_STORE) {
+        constexpr bool OUT16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16);
+        constexpr int CH_COLS = OUT16 ? 64 : 32;  // one chunk = 128 bytes per row
+        const uint32_t ring = smem_u32(epi_stage) + static_cast<uint32_t>(q * C::EPI_SLOTS * 4096);
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / CH_COLS; ++c) {
+          // the bulk store that last used this slot must have finished reading it
+          if (lane == 0) tma_store_wait_read<C::EPI_SLOTS - 1>();
+          __syncwarp();
+          const uint32_t row_addr = ring + static_cast<uint32_t>(epi_slot * 4096 + lane * 128);
+          if constexpr (OUT16) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 64 + h * 32), r);
+              tmem_ld_wait();
+              uint32_t w[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float v0 = __uint_as_float(r[j]) + bias_s[c * 64 + h * 32 + j];
+                float v1 = __uint_as_float(r[j + 1]) + bias_s[c * 64 + h * 32 + j + 1];
+                if constexpr (EPI == EPI_BIAS_QGELU_BF16) {
+                  v0 = quick_gelu(v0);
+                  v1 = quick_gelu(v1);
+                }
+                w[j >> 1] = pack_bf16x2(v0, v1);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // 16-byte chunk (h*4 + k) of this row, 128B-swizzled
+                st_shared_v4(row_addr + ((static_cast<uint32_t>(h * 4 + k) ^ sw) << 4), w[4 * k], w[4 * k + 1],
+                             w[4 * k + 2], w[4 * k + 3]);
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(__uint_as_float(r[4 * k + e]) + bias_s[c * 32 + 4 * k + e]);
+              st_shared_v4(row_addr + ((static_cast<uint32_t>(k) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_c, ring + static_cast<uint32_t>(epi_slot * 4096), col0 + c * CH_COLS, row0);
+            tma_store_commit();
+          }
+          epi_slot = (epi_slot + 1 == C::EPI_SLOTS) ? 0 : epi_slot + 1;
+        }
+      } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll 1
         for (int g = 0; g < BLOCK_N / 64; ++g) {
@@ -258,6 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // bias_s free for the next tile
     }
+    if constexpr (TMA_STORE) {
+      if (lane == 0) tma_store_wait_read<0>();  // smem must stay valid until the last bulk store has read it
+    }
+    (void)epi_slot;
   }
 
   tc_fence_before();
@@ -285,26 +356,27 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (cols contiguous, row stride ld elements); box = [BLOCK_K cols, box_rows rows].
-int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+// 2-D row-major [rows, cols] (cols contiguous, row stride ld elements) of bf16 (elem_bytes 2) or fp32 (4);
+// box = [128 bytes of columns, box_rows rows], SWIZZLE_128B.
+int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows, int elem_bytes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return 0;
 }
 
-template <int BLOCK_N, int EPI>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+template <int BLOCK_N, int EPI, bool TMA_STORE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& args, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = gemm_kernel<BLOCK_N, EPI>;
+  auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE>;
   if (!configured) {
     HH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
@@ -312,18 +384,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, c
   const int total = args.tiles_m * args.tiles_n;
   int grid = num_sms();
   if (grid > total) grid = total;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, args);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, args);
   HH_CHECK_LAUNCH("gemm_kernel");
   return 0;
 }
 
 template <int BLOCK_N>
-int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, int epi, cudaStream_t stream) {
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, bool tma_store, const GemmArgs& args,
+                 int epi, cudaStream_t stream) {
+  if (tma_store) {
+    switch (epi) {
+      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true>(ta, tb, tc, args, stream);
+    }
+  }
   switch (epi) {
-    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16>(ta, tb, args, stream);
-    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16>(ta, tb, args, stream);
-    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32>(ta, tb, args, stream);
-    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32>(ta, tb, args, stream);
+    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, false>(ta, tb, tc, args, stream);
   }
   return fail(-2, "gemm_bf16: unknown epilogue");
 }
@@ -348,11 +428,21 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   int bn = 256;
   if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || tiles_m * ((N + 255) / 256) < num_sms()) bn = 128;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
   if (rc) return rc;
   rc = make_tmap(&tb, W, N, K, ldw, bn);
   if (rc) return rc;
+  // bulk-tensor stores need a 16-byte aligned base and row pitch; the residual epilogue reads while it writes
+  const int esz = out_bf16 ? 2 : 4;
+  const bool tma_store = epilogue != EPI_BIAS_RES_F32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                         (static_cast<size_t>(ldc) * esz) % 16 == 0;
+  if (tma_store) {
+    rc = make_tmap(&tc, out, M, N, ldc, 32, esz);
+    if (rc) return rc;
+  } else {
+    tc = ta;
+  }
 
   GemmArgs args;
   args.out = out;
@@ -365,8 +455,8 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   args.ldr = ldr;
   args.tiles_m = tiles_m;
   args.tiles_n = (N + bn - 1) / bn;
-  if (bn == 256) return dispatch_epi<256>(ta, tb, args, epilogue, stream);
-  return dispatch_epi<128>(ta, tb, args, epilogue, stream);
+  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, args, epilogue, stream);
+  return dispatch_epi<128>(ta, tb, tc, tma_store, args, epilogue, stream);
 }
 
 }  // namespace hh

@@ -52,6 +52,8 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
 //   out_f32 [M,D], out_bf16 [M,D], and out2 = y + post_add[row % post_mod] (bf16 and/or f32).
 struct LnArgs {
   const float* x; int ldx;
+  const bf16* delta;    // optional bf16 [M, D]: the norm is taken of x + delta (fused residual add)
+  float* xsum_out;      // optional fp32 [M, D]: receives x + delta (may alias x)
   const float* w; const float* b; float eps;
   float* out_f32; bf16* out_bf16;
   const float* post_add; int post_mod;   // optional positional term added after the norm

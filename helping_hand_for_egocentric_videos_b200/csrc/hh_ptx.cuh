@@ -79,9 +79,9 @@ __device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint64_t*
       : "memory");
 }
 // 2-D tiled store shared -> global (bulk async group).
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int crd0, int crd1) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int crd0, int crd1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(crd0), "r"(crd1)
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(crd0), "r"(crd1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -21,7 +21,14 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
 #pragma unroll
   for (int j = 0; j < LN_MAX_VEC; ++j) {
     if (j < nv) {
-      v[j] = *reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4);
+      const int c = (j * 32 + lane) * 4;
+      v[j] = *reinterpret_cast<const float4*>(xr + c);
+      if (a.delta) {  // residual branch output (bf16) folded in here: x <- x + delta
+        const uint2 d = *reinterpret_cast<const uint2*>(a.delta + static_cast<size_t>(warp) * a.D + c);
+        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
+        v[j].x += d0.x; v[j].y += d0.y; v[j].z += d1.x; v[j].w += d1.y;
+        if (a.xsum_out) *reinterpret_cast<float4*>(a.xsum_out + static_cast<size_t>(warp) * a.D + c) = v[j];
+      }
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
   }
