@@ -3,7 +3,9 @@
 // (n x 64 bf16 each) and Q stay resident in shared memory, 8 warps run a flash-style loop with legacy warp MMA
 // (mma.sync m16n8k16, fp32 accumulate, fp32 online softmax in the exp2 domain).  The CLS key/value initialise the
 // running softmax state (m = q.k_cls, l = 1, O = v_cls), so the key loop only sees the n patch keys.
-// The CLS *query* row is produced by attn_cls (attn_time.cu).
+// The CLS *query* (which attends all 1+T*n keys, LaviLa.py:258) rides along as one extra 16-row block per CTA whose
+// only live row is q_cls: its (max, sum, o[64]) over this frame's keys is written as a partial per (clip, head, frame)
+// and folded, with the CLS key itself, into output row 0 by attn_cls_merge (attn_time.cu).
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
 
@@ -15,8 +17,8 @@ constexpr int HD = 64;
 constexpr int LDS = 72;  // smem row stride in bf16 (144 B): 16-byte aligned rows, conflict-free ldmatrix
 constexpr float LOG2E = 1.4426950408889634f;
 
-__global__ void __launch_bounds__(256)
-attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int n, int H) {
+__global__ void __launch_bounds__(256, 2)
+attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ cls_part, int T, int n, int H) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int D = H * HD;
   const int N = 1 + T * n;
@@ -28,8 +30,8 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
   const int qrows = mblocks * 16;
   const int krows = kblocks * 64;
 
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
-  bf16* Ks = Qs + qrows * LDS;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);          // qrows patch queries + 16 rows for the CLS-query block
+  bf16* Ks = Qs + (qrows + 16) * LDS;
   bf16* Vs = Ks + krows * LDS;
   float* kcls = reinterpret_cast<float*>(Vs + krows * LDS);
   float* vcls = kcls + HD;
@@ -51,11 +53,17 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
       cp_async_16(Vs + r * LDS + ch * 8, src + 2 * D, valid);
     }
   }
-  cp_async_commit();
-  if (tid < 2 * HD) {
+  {  // CLS-query block: row qrows = q_cls, rows qrows+1 .. qrows+15 = 0
     const bf16* cls = qkv + static_cast<size_t>(b) * N * ld + h * HD;
-    if (tid < HD) kcls[tid] = __bfloat162float(cls[D + tid]);
-    else vcls[tid - HD] = __bfloat162float(cls[2 * D + tid - HD]);
+    if (tid < 16 * 8) {
+      const int r = tid >> 3, ch = tid & 7;
+      cp_async_16(Qs + (qrows + r) * LDS + ch * 8, cls + ch * 8, r == 0);
+    }
+    cp_async_commit();
+    if (tid < 2 * HD) {
+      if (tid < HD) kcls[tid] = __bfloat162float(cls[D + tid]);
+      else vcls[tid - HD] = __bfloat162float(cls[2 * D + tid - HD]);
+    }
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -63,7 +71,8 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, lr = lane & 7;
 
-  for (int mb = warp; mb < mblocks; mb += 8) {
+  for (int mb = warp; mb <= mblocks; mb += 8) {  // block `mblocks` is the CLS query
+    const bool is_cls = (mb == mblocks);
     const int r0 = mb * 16;
     // Q fragments for the 4 k-steps over d
     uint32_t qf[4][4];
@@ -92,6 +101,12 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
     for (int ni = 0; ni < 8; ++ni) {
       o[ni][0] = o[ni][2] = vcls[ni * 8 + 2 * t];
       o[ni][1] = o[ni][3] = vcls[ni * 8 + 2 * t + 1];
+    }
+    if (is_cls) {  // the CLS query's partial covers this frame's patch keys only: empty initial state
+      m0 = m1 = -INFINITY;
+      l0 = l1 = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) o[ni][0] = o[ni][1] = o[ni][2] = o[ni][3] = 0.f;
     }
 
     for (int kb = 0; kb < kblocks; ++kb) {
@@ -154,6 +169,21 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (is_cls) {  // unnormalised partial (m, l, o[64]) of row 0 -> workspace [b][h][f]
+      if (g == 0) {
+        float* dst = cls_part + ((static_cast<size_t>(b) * H + h) * T + f) * (HD + 2);
+        if (t == 0) {
+          dst[0] = m0;
+          dst[1] = l0;
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          dst[2 + ni * 8 + 2 * t] = o[ni][0];
+          dst[2 + ni * 8 + 2 * t + 1] = o[ni][1];
+        }
+      }
+      continue;
+    }
     const float i0 = 1.f / l0, i1 = 1.f / l1;
 
     // ---- stage the 16x64 result in this warp's (now free) Q rows, then 16-byte coalesced row stores
@@ -179,10 +209,11 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, i
 
 }  // namespace
 
-int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStream_t stream) {
+int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream) {
   HH_REQUIRE(B > 0 && T > 0 && n > 0 && H > 0, "attn_space: empty problem");
+  HH_REQUIRE(cls_ws != nullptr, "attn_space: CLS workspace");
   const int mblocks = (n + 15) / 16, kblocks = (n + 63) / 64;
-  const size_t smem = static_cast<size_t>(mblocks * 16 + 2 * kblocks * 64) * LDS * sizeof(bf16) + 2 * HD * sizeof(float);
+  const size_t smem = static_cast<size_t>(mblocks * 16 + 16 + 2 * kblocks * 64) * LDS * sizeof(bf16) + 2 * HD * sizeof(float);
   HH_REQUIRE(smem <= 227 * 1024, "attn_space: patches per frame too large for the resident-K/V kernel");
   static size_t configured = 0;
   if (smem > configured) {
@@ -190,9 +221,9 @@ int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStrea
                                        static_cast<int>(smem)));
     configured = smem;
   }
-  attn_space_kernel<<<B * T * H, 256, smem, stream>>>(qkv, out, T, n, H);
+  attn_space_kernel<<<B * T * H, 256, smem, stream>>>(qkv, out, cls_ws, T, n, H);
   HH_CHECK_LAUNCH("attn_space_kernel");
-  return 0;
+  return attn_cls_merge(qkv, cls_ws, out, B, 1 + T * n, H, T, stream);
 }
 
 }  // namespace hh

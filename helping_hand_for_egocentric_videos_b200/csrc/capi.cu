@@ -170,14 +170,19 @@ int hh_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   return f32_to_bf16(src, static_cast<bf16*>(dst), static_cast<size_t>(n), S(stream));
 }
 int hh_attention(const void* qkv, void* out, int B, int T, int n, int H, int kind, void* stream) {
+  HH_GUARD_BEGIN
   const bf16* q = static_cast<const bf16*>(qkv);
   bf16* o = static_cast<bf16*>(out);
+  static thread_local DevBuf ws;
+  int rc = ws.reserve(attn_cls_workspace_bytes(B, T, n, H));
+  if (rc) return rc;
   switch (kind) {
-    case 0: return attn_space(q, o, B, T, n, H, S(stream));
-    case 1: return attn_time(q, o, B, T, n, H, S(stream));
+    case 0: return attn_space(q, o, B, T, n, H, static_cast<float*>(ws.ptr), S(stream));
+    case 1: return attn_time(q, o, B, T, n, H, static_cast<float*>(ws.ptr), S(stream));
     case 2: return attn_cls(q, o, B, 1 + T * n, H, S(stream));
   }
-  return fail(-2, "hh_attention: kind must be 0 (space), 1 (time) or 2 (cls)");
+  return fail(-2, "hh_attention: kind must be 0 (space), 1 (time) or 2 (stand-alone CLS row)");
+  HH_GUARD_END
 }
 int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
                        int S_, void* stream) {

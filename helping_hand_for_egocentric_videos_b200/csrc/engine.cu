@@ -217,6 +217,7 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
   RC(ws_a.reserve(Mc * D * 2));
   RC(ws_qkv.reserve(Mc * 3 * D * 2));
   RC(ws_h.reserve(Mc * Hd * 2));
+  RC(ws_cls.reserve(attn_cls_workspace_bytes(chunk, T, n, H)));
   bf16* patches = static_cast<bf16*>(ws_patches.ptr);
   float* tok = static_cast<float*>(ws_tok.ptr);
   float* x = static_cast<float*>(ws_x.ptr);
@@ -224,6 +225,7 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
   bf16* a = static_cast<bf16*>(ws_a.ptr);
   bf16* qkv = static_cast<bf16*>(ws_qkv.ptr);
   bf16* h = static_cast<bf16*>(ws_h.ptr);
+  float* cls_ws = static_cast<float*>(ws_cls.ptr);
   const size_t frame_elems = static_cast<size_t>(3) * cfg.img_size * cfg.img_size;
 
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -269,9 +271,8 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
         else RC(ln_fused(dl, false, p + "norm1", 1e-6f, a, nullptr));
         PROF(K_GEMM_QKV, gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
                                    static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
-        if (at == 0) PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, s));
-        else PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, s));
-        PROF(K_ATTN_CLS, attn_cls(qkv, a, Bc, N, H, s));
+        if (at == 0) PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, cls_ws, s));
+        else PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, cls_ws, s));
         PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, dl, D,
                                     weights.get(q + ".proj.bias"), nullptr, 0, M, D, D, EPI_BIAS_BF16, s));
         launches += 5;

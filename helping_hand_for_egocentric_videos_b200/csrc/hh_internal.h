@@ -75,9 +75,13 @@ int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, con
 
 // ---------------------------------------------------------------- divided space-time attention (attn_*.cu)
 // qkv bf16 [B*N, 3*D] (q pre-scaled), N = 1 + T*n, heads of 64. out bf16 [B*N, D]; patch rows only.
-int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStream_t stream);
-int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, cudaStream_t stream);
-// CLS query row: attends all N keys (both attention kinds). Writes out[b*N + 0].
+// Both write every row of out, including the CLS query row (out[b*N + 0]), which attends all N keys; its partial
+// softmax states go through `cls_ws` (attn_cls_workspace_bytes) and are folded by attn_cls_merge.
+size_t attn_cls_workspace_bytes(int B, int T, int n, int H);
+int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
+int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
+int attn_cls_merge(const bf16* qkv, const float* parts, bf16* out, int B, int N, int H, int nparts, cudaStream_t stream);
+// Stand-alone CLS query row (reference statement of the fused path; used when T > 16).
 int attn_cls(const bf16* qkv, bf16* out, int B, int N, int H, cudaStream_t stream);
 
 // ---------------------------------------------------------------- decoder satellites (decoder.cu)

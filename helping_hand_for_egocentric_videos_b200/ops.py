@@ -48,9 +48,10 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, wan
     return o32, o16
 
 
-def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int) -> torch.Tensor:
-    """Divided space-time attention pieces on packed qkv (bf16 [B*(1+T*n), 3*H*64], q pre-scaled).
-    Returns dict of outputs for kind 'space', 'time' (patch rows) with the CLS row filled in both."""
+def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int, standalone_cls: bool = False) -> dict:
+    """Divided space-time attention on packed qkv (bf16 [B*(1+T*n), 3*H*64], q pre-scaled).
+    Returns {'space': o, 'time': o} with every row filled (patch rows + the CLS query row).  With
+    `standalone_cls` the CLS row is overwritten by the stand-alone CLS kernel (kind 2)."""
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
     N = 1 + T * n
     outs = {}
@@ -58,7 +59,8 @@ def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int) -> torch.Tensor
     for kind, name in ((0, "space"), (1, "time")):
         o = torch.zeros(B * N, H * 64, dtype=torch.bfloat16, device=qkv.device)
         L.check(lib.hh_attention(L.ptr(qkv), L.ptr(o), B, T, n, H, kind, L.stream_ptr()), "hh_attention")
-        L.check(lib.hh_attention(L.ptr(qkv), L.ptr(o), B, T, n, H, 2, L.stream_ptr()), "hh_attention(cls)")
+        if standalone_cls:
+            L.check(lib.hh_attention(L.ptr(qkv), L.ptr(o), B, T, n, H, 2, L.stream_ptr()), "hh_attention(cls)")
         outs[name] = o
     return outs
 

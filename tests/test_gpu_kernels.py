@@ -123,10 +123,15 @@ def test_divided_attention(B, T, n, H):
     qkv[:, :H * 64] *= 0.35            # plausible pre-scaled q magnitude
     qkv = qkv.bfloat16()
     outs = ops.attention(qkv, B, T, n, H)
+    alone = ops.attention(qkv, B, T, n, H, standalone_cls=True)
     for mode in ("space", "time"):
         ref = _ref_attention(qkv, B, T, n, H, mode)
         # P is rounded to bf16 before P.V in the tensor-core kernel: allow 2^-7 relative on O(1) outputs
         _close(outs[mode], ref, 2 ** -6, 6e-3, "attention %s" % mode)
+        _close(alone[mode], ref, 2 ** -6, 6e-3, "attention %s (stand-alone CLS row)" % mode)
+        cls_rows = torch.arange(B, device=qkv.device) * N
+        # the CLS query sees all N keys: its output is a near-uniform average, so check it on its own scale
+        _close(outs[mode][cls_rows], ref[cls_rows], 2 ** -6, 1e-3, "CLS row %s" % mode)
 
 
 @pytest.mark.parametrize("B,Q,heads,S", [(2, 5, 2, 48), (1, 13, 8, 4096), (3, 13, 8, 784), (2, 16, 1, 100), (1, 1, 2, 31)])
