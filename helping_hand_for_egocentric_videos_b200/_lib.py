@@ -62,6 +62,7 @@ SIGNATURES = {
     "hh_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
     "hh_attention": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "hh_cross_attention": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "hh_cross_attention_simt": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "hh_comm_unique_id": (_i, [_p]),
     "hh_comm_create": (_i, [C.POINTER(_p), _i, _i, _p]),
     "hh_comm_destroy": (_i, [_p]),

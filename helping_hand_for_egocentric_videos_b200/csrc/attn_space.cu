@@ -125,11 +125,16 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* _
       }
       // mask keys past n (only possible in the last block), row max
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (kb * 64 + 64 > n) {  // ragged last block only (n = 196); n = 256 never takes this path
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          const int key = kb * 64 + ni * 8 + 2 * t;
+          if (key >= n) s[ni][0] = s[ni][2] = -INFINITY;
+          if (key + 1 >= n) s[ni][1] = s[ni][3] = -INFINITY;
+        }
+      }
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
-        const int key = kb * 64 + ni * 8 + 2 * t;
-        if (key >= n) s[ni][0] = s[ni][2] = -INFINITY;
-        if (key + 1 >= n) s[ni][1] = s[ni][3] = -INFINITY;
         mx0 = fmaxf(mx0, fmaxf(s[ni][0], s[ni][1]));
         mx1 = fmaxf(mx1, fmaxf(s[ni][2], s[ni][3]));
       }
@@ -138,7 +143,8 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* _
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: m0/m1 start finite
-      const float c0 = exp2f((m0 - mn0) * LOG2E), c1 = exp2f((m1 - mn1) * LOG2E);
+      const float ml0 = mn0 * LOG2E, ml1 = mn1 * LOG2E;
+      const float c0 = fast_exp2(m0 * LOG2E - ml0), c1 = fast_exp2(m1 * LOG2E - ml1);
       m0 = mn0;
       m1 = mn1;
       l0 *= c0;
@@ -146,8 +152,8 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* _
       uint32_t pa[4][4];
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni) {
-        const float p0 = exp2f((s[ni][0] - mn0) * LOG2E), p1 = exp2f((s[ni][1] - mn0) * LOG2E);
-        const float p2 = exp2f((s[ni][2] - mn1) * LOG2E), p3 = exp2f((s[ni][3] - mn1) * LOG2E);
+        const float p0 = fast_exp2(fmaf(s[ni][0], LOG2E, -ml0)), p1 = fast_exp2(fmaf(s[ni][1], LOG2E, -ml0));
+        const float p2 = fast_exp2(fmaf(s[ni][2], LOG2E, -ml1)), p3 = fast_exp2(fmaf(s[ni][3], LOG2E, -ml1));
         l0 += p0 + p1;
         l1 += p2 + p3;
         pa[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(p0, p1);

@@ -130,8 +130,8 @@ attn_time_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
     uint32_t pa[2][4];
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni) {
-      const float p0 = exp2f((s[0][ni][0] - mx0) * LOG2E), p1 = exp2f((s[0][ni][1] - mx0) * LOG2E);
-      const float p2 = exp2f((s[0][ni][2] - mx1) * LOG2E), p3 = exp2f((s[0][ni][3] - mx1) * LOG2E);
+      const float p0 = fast_exp2(fmaf(s[0][ni][0], LOG2E, -mx0 * LOG2E)), p1 = fast_exp2(fmaf(s[0][ni][1], LOG2E, -mx0 * LOG2E));
+      const float p2 = fast_exp2(fmaf(s[0][ni][2], LOG2E, -mx1 * LOG2E)), p3 = fast_exp2(fmaf(s[0][ni][3], LOG2E, -mx1 * LOG2E));
       l0 += p0 + p1;
       l1 += p2 + p3;
       pa[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -156,13 +156,13 @@ attn_time_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
     cmx = fmaxf(cmx, __shfl_xor_sync(0xffffffffu, cmx, 1));
     cmx = fmaxf(cmx, __shfl_xor_sync(0xffffffffu, cmx, 2));
     const float cmn = fmaxf(cm, cmx);  // finite: T >= 1 gives at least one valid key
-    const float ccorr = exp2f((cm - cmn) * LOG2E);
+    const float ccorr = fast_exp2((cm - cmn) * LOG2E);
     cm = cmn;
     cl *= ccorr;
     uint32_t pc[2][4];
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni) {
-      const float p0 = exp2f((s[1][ni][0] - cmn) * LOG2E), p1 = exp2f((s[1][ni][1] - cmn) * LOG2E);
+      const float p0 = fast_exp2(fmaf(s[1][ni][0], LOG2E, -cmn * LOG2E)), p1 = fast_exp2(fmaf(s[1][ni][1], LOG2E, -cmn * LOG2E));
       cl += p0 + p1;
       pc[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(p0, p1);
       pc[ni >> 1][(ni & 1) * 2 + 1] = 0u;  // rows g+8 of block 1 are dead

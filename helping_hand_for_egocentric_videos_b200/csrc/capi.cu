@@ -195,6 +195,17 @@ int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, f
   HH_GUARD_END
 }
 
+int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
+                            int S_, void* stream) {
+  HH_GUARD_BEGIN
+  static thread_local DevBuf ws;
+  int rc = ws.reserve(cross_attn_simt_workspace_bytes(B, Q, heads, S_));
+  if (rc) return rc;
+  return cross_attn_simt(q, static_cast<const bf16*>(K), static_cast<const bf16*>(V), ldkv, out, B, Q, heads, S_, ws.ptr,
+                         S(stream));
+  HH_GUARD_END
+}
+
 // ------------------------------------------------------------------------------------------ NCCL all-gather
 namespace {
 typedef int (*nccl_get_uid_t)(void*);

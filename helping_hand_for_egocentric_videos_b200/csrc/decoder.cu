@@ -354,13 +354,14 @@ int self_attn_queries(const float* q, const float* k, const float* v, int ld, fl
   return 0;
 }
 
-size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S) {
+size_t cross_attn_simt_workspace_bytes(int B, int Q, int heads, int S) {
   (void)Q;
   return static_cast<size_t>(B) * heads * cross_splits(B, heads, S) * XQ * XPART * sizeof(float);
 }
 
-int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
-               void* workspace, cudaStream_t stream) {
+// fp32 SIMT statement of the cross attention (kept as a second implementation for differential tests)
+int cross_attn_simt(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
+                    void* workspace, cudaStream_t stream) {
   HH_REQUIRE(Q >= 1 && Q <= XQ, "cross_attn: 1..16 queries supported");
   HH_REQUIRE(ldkv % 8 == 0, "cross_attn: K/V row stride must be a multiple of 8 elements");
   HH_REQUIRE(workspace != nullptr, "cross_attn: workspace");

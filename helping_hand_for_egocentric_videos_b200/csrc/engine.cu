@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace hh {
@@ -127,6 +128,10 @@ int Profiler::collect(double* ms, int* counts) {
 
 // ========================================================================================== encoder
 Encoder::Encoder(const hh_encoder_cfg& c) : cfg(c) {
+  if (const char* e = std::getenv("HH_ENCODER_CHUNK")) {  // clips per pass through the workspace (tuning knob)
+    const int v = std::atoi(e);
+    if (v > 0) max_chunk = v;
+  }
   grid = cfg.img_size / cfg.patch_size;
   n = grid * grid;
   N = 1 + cfg.num_frames * n;

@@ -105,6 +105,9 @@ int self_attn_queries(const float* q, const float* k, const float* v, int ld, fl
 size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S);
 int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
                void* workspace, cudaStream_t stream);
+size_t cross_attn_simt_workspace_bytes(int B, int Q, int heads, int S);
+int cross_attn_simt(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
+                    void* workspace, cudaStream_t stream);
 // boxes[l, b*T+t, q, :] head input: cond = hsproj[l,b,q,:] + frameterm[t,:]  (ObjDecoder frame_proj split)
 int add_frame_term(const float* hsproj, const float* frameterm, float* out, int LB, int T, int Q, int C,
                    cudaStream_t stream);

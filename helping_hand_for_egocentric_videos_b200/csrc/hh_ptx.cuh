@@ -201,6 +201,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
   return __bfloat1622float2(v);
 }
 
+// 2^x on the MUFU pipe without the denormal / range fix-up code of exp2f (ex2.approx.ftz: 2^-inf = +0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -17,21 +17,35 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
   const int nv = a.D >> 7;  // float4 per lane
   const float* xr = a.x + static_cast<size_t>(warp) * a.ldx;
   float4 v[LN_MAX_VEC];
+  uint2 dv[LN_MAX_VEC];
   float s = 0.f;
+  // All loads of the row are issued before anything is stored: xsum_out may alias x, and a store in between would
+  // serialise the loads behind it.  Streaming (evict-first) accesses: every byte here is touched exactly once.
 #pragma unroll
-  for (int j = 0; j < LN_MAX_VEC; ++j) {
-    if (j < nv) {
-      const int c = (j * 32 + lane) * 4;
-      v[j] = *reinterpret_cast<const float4*>(xr + c);
-      if (a.delta) {  // residual branch output (bf16) folded in here: x <- x + delta
-        const uint2 d = *reinterpret_cast<const uint2*>(a.delta + static_cast<size_t>(warp) * a.D + c);
-        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
+  for (int j = 0; j < LN_MAX_VEC; ++j)
+    if (j < nv) v[j] = __ldcs(reinterpret_cast<const float4*>(xr + (j * 32 + lane) * 4));
+  if (a.delta) {  // residual branch output (bf16) folded in here: x <- x + delta
+    const bf16* dr = a.delta + static_cast<size_t>(warp) * a.D;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j)
+      if (j < nv) dv[j] = __ldcs(reinterpret_cast<const uint2*>(dr + (j * 32 + lane) * 4));
+#pragma unroll
+    for (int j = 0; j < LN_MAX_VEC; ++j) {
+      if (j < nv) {
+        const float2 d0 = unpack_bf16x2(dv[j].x), d1 = unpack_bf16x2(dv[j].y);
         v[j].x += d0.x; v[j].y += d0.y; v[j].z += d1.x; v[j].w += d1.y;
-        if (a.xsum_out) *reinterpret_cast<float4*>(a.xsum_out + static_cast<size_t>(warp) * a.D + c) = v[j];
       }
-      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    if (a.xsum_out) {
+      float* xo = a.xsum_out + static_cast<size_t>(warp) * a.D;
+#pragma unroll
+      for (int j = 0; j < LN_MAX_VEC; ++j)
+        if (j < nv) __stcs(reinterpret_cast<float4*>(xo + (j * 32 + lane) * 4), v[j]);
     }
   }
+#pragma unroll
+  for (int j = 0; j < LN_MAX_VEC; ++j)
+    if (j < nv) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   const float mean = warp_sum(s) / static_cast<float>(a.D);
   float ss = 0.f;
 #pragma unroll
@@ -48,8 +62,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
   for (int j = 0; j < LN_MAX_VEC; ++j) {
     if (j < nv) {
       const int c = (j * 32 + lane) * 4;
-      const float4 w = *reinterpret_cast<const float4*>(a.w + c);
-      const float4 b = *reinterpret_cast<const float4*>(a.b + c);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(a.w + c));  // read-only path: not ordered behind the stores
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.b + c));
       float4 y;
       y.x = v[j].x * rstd * w.x + b.x;
       y.y = v[j].y * rstd * w.y + b.y;

@@ -65,13 +65,15 @@ def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int, standalone_cls:
     return outs
 
 
-def cross_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, B: int, Q: int, heads: int, S: int) -> torch.Tensor:
-    """q fp32 [B*Q, heads*64] (pre-scaled); K, V bf16 [B*S, heads*64]."""
+def cross_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, B: int, Q: int, heads: int, S: int,
+                    simt: bool = False) -> torch.Tensor:
+    """q fp32 [B*Q, heads*64] (pre-scaled); K, V bf16 [B*S, heads*64].  `simt` selects the fp32 SIMT statement."""
     q = _f32(q)
     assert K.dtype == torch.bfloat16 and V.dtype == torch.bfloat16 and K.is_contiguous() and V.is_contiguous()
     out = torch.empty_like(q)
-    L.check(L.load().hh_cross_attention(L.ptr(q), L.ptr(K), L.ptr(V), K.shape[1], L.ptr(out), B, Q, heads, S,
-                                        L.stream_ptr()), "hh_cross_attention")
+    fn = L.load().hh_cross_attention_simt if simt else L.load().hh_cross_attention
+    L.check(fn(L.ptr(q), L.ptr(K), L.ptr(V), K.shape[1], L.ptr(out), B, Q, heads, S, L.stream_ptr()),
+            "hh_cross_attention")
     return out
 
 

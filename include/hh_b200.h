@@ -144,6 +144,9 @@ int hh_attention(const void* qkv, void* out, int B, int T, int n, int H, int kin
 /* Query->patch cross attention (tfm_decoder.py:438-441 core): q fp32 [B*Q, heads*64] pre-scaled, K/V bf16 [B*S, ldkv]. */
 int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
                        int S, void* stream);
+/* Same operator on the fp32 SIMT kernel (second implementation kept for differential testing). */
+int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
+                            int S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Data-parallel exchange: the one collective of the path (all-gather of embeddings for the cross-rank similarity

@@ -146,7 +146,11 @@ def test_cross_attention(B, Q, heads, S):
     kh = K.float().view(B, S, heads, 64).transpose(1, 2)
     vh = V.float().view(B, S, heads, 64).transpose(1, 2)
     ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).transpose(1, 2).reshape(B * Q, C_)
-    _close(got, ref, 1e-4, 2e-5, "cross attention")
+    # P is rounded to bf16 for the P.V tensor-core product (q enters as a bf16 hi+lo pair, so logits are fp32-accurate)
+    # With few keys the softmax is peaked (p up to ~0.5), so the bf16 rounding of P costs up to 2^-9 * p * |v| ~ 3e-3.
+    _close(got, ref, 2 ** -7, 4e-3, "cross attention")
+    simt = ops.cross_attention(q, K, V, B, Q, heads, S, simt=True)     # fp32 SIMT statement of the same kernel
+    _close(simt, ref, 1e-4, 2e-5, "cross attention (SIMT)")
 
 
 @pytest.mark.parametrize("R,N,K", [(13, 512, 512), (832, 2048, 512), (65, 4, 512), (7, 256, 768), (100, 100, 32)])
