@@ -15,6 +15,7 @@
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -67,7 +68,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // TMA_STORE: the epilogue writes 32-row x 128-byte boxes through shared memory with cp.async.bulk.tensor stores
 // (needs a 16-byte aligned output with a 16-byte multiple row pitch); otherwise rows are stored directly.
-template <int BLOCK_N, int EPI, bool TMA_STORE>
+// CLUSTER: CTAs are launched as pairs (cluster 2x1x1) that work on two vertically adjacent output tiles with the SAME
+// weight tile: each CTA fetches half of the W tile and multicasts it into both CTAs' shared memory, which cuts the
+// L2 -> SM operand traffic per tile from A + W to A + W/2 (-33 %).  A stage is released to the producers only after
+// BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto both empty barriers).
+template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const GemmArgs p) {
@@ -88,7 +93,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  // tile walk: a CTA (or CTA pair) takes every tile_step-th (pair of) tile(s); n_blk varies fastest
+  const int cta_rank = CLUSTER ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile_first = CLUSTER ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CLUSTER ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_tiles = CLUSTER ? ((p.tiles_m + 1) >> 1) * p.tiles_n : p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -98,7 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CLUSTER ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -112,6 +121,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -120,16 +130,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n;
-        const int n_blk = tile - m_blk * p.tiles_n;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int mp = tile / p.tiles_n;
+        const int n_blk = tile - mp * p.tiles_n;
+        const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          if constexpr (CLUSTER) {  // my half of the W tile, into both CTAs (box = BLOCK_N/2 rows)
+            tma_load_2d_mcast(&tma_b, &full_bar[stage], sb + cta_rank * (C::B_BYTES / 2), kb * BLOCK_K,
+                              n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2), static_cast<uint16_t>(3));
+          } else {
+            tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -145,7 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -162,7 +178,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in a pair: tell both CTAs' producers)
+          if constexpr (CLUSTER) umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>(3));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -183,9 +201,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     int epi_slot = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n;
-      const int n_blk = tile - m_blk * p.tiles_n;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const int mp = tile / p.tiles_n;
+      const int n_blk = tile - mp * p.tiles_n;
+      const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
       const int row0 = m_blk * BLOCK_M + q * 32;
       const int col0 = n_blk * BLOCK_N;
 
@@ -333,6 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -372,14 +392,33 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
   return 0;
 }
 
-template <int BLOCK_N, int EPI, bool TMA_STORE>
+template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& args, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE>;
+  auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE, CLUSTER>;
   if (!configured) {
     HH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
+  }
+  if constexpr (CLUSTER) {
+    const int pairs = ((args.tiles_m + 1) / 2) * args.tiles_n;
+    int grid = num_sms() & ~1;
+    if (grid > 2 * pairs) grid = 2 * pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, args));
+    return 0;
   }
   const int total = args.tiles_m * args.tiles_n;
   int grid = num_sms();
@@ -390,20 +429,27 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 }
 
 template <int BLOCK_N>
-int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, bool tma_store, const GemmArgs& args,
-                 int epi, cudaStream_t stream) {
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, bool tma_store, bool cluster,
+                 const GemmArgs& args, int epi, cudaStream_t stream) {
+  if (tma_store && cluster) {
+    switch (epi) {
+      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, true>(ta, tb, tc, args, stream);
+    }
+  }
   if (tma_store) {
     switch (epi) {
-      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true>(ta, tb, tc, args, stream);
-      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true>(ta, tb, tc, args, stream);
-      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, false>(ta, tb, tc, args, stream);
+      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, false>(ta, tb, tc, args, stream);
+      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, false>(ta, tb, tc, args, stream);
     }
   }
   switch (epi) {
-    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, false, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, false, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32, false, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, false, false>(ta, tb, tc, args, stream);
   }
   return fail(-2, "gemm_bf16: unknown epilogue");
 }
@@ -428,15 +474,18 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   int bn = 256;
   if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || tiles_m * ((N + 255) / 256) < num_sms()) bn = 128;
 
-  CUtensorMap ta, tb, tc;
-  int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
-  if (rc) return rc;
-  rc = make_tmap(&tb, W, N, K, ldw, bn);
-  if (rc) return rc;
   // bulk-tensor stores need a 16-byte aligned base and row pitch; the residual epilogue reads while it writes
   const int esz = out_bf16 ? 2 : 4;
   const bool tma_store = epilogue != EPI_BIAS_RES_F32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                          (static_cast<size_t>(ldc) * esz) % 16 == 0;
+  // CTA pairs sharing the W tile (multicast) once there are enough row tiles to pair up
+  static const bool cluster_ok = std::getenv("HH_GEMM_NO_CLUSTER") == nullptr;
+  const bool cluster = cluster_ok && tma_store && tiles_m >= num_sms() / 2 && (num_sms() % 2 == 0);
+  CUtensorMap ta, tb, tc;
+  int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tb, W, N, K, ldw, cluster ? bn / 2 : bn);
+  if (rc) return rc;
   if (tma_store) {
     rc = make_tmap(&tc, out, M, N, ldc, 32, esz);
     if (rc) return rc;
@@ -455,8 +504,8 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   args.ldr = ldr;
   args.tiles_m = tiles_m;
   args.tiles_n = (N + bn - 1) / bn;
-  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, args, epilogue, stream);
-  return dispatch_epi<128>(ta, tb, tc, tma_store, args, epilogue, stream);
+  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, cluster, args, epilogue, stream);
+  return dispatch_epi<128>(ta, tb, tc, tma_store, cluster, args, epilogue, stream);
 }
 
 }  // namespace hh

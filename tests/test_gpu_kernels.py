@@ -38,6 +38,8 @@ GEMM_SHAPES = [
     (128, 256, 64), (300, 3072, 1024), (4097, 1024, 1024), (1000, 4096, 1024), (515, 1024, 4096),
     (777, 768, 768), (260, 2304, 768), (1568, 1024, 640), (100, 22048, 512), (4100, 6144, 512), (65, 128, 128),
     (129, 96, 72), (1, 8, 8),
+    # M >= 74 row tiles: CTA-pair path (W tile multicast across a 2-CTA cluster); odd and even tile counts, ragged tails
+    (9600, 512, 256), (9601, 1024, 1024), (12288, 3072, 128), (20000, 256, 4096), (9473, 384, 64),
 ]
 
 
