@@ -218,6 +218,7 @@ attn_space_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* _
 int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream) {
   HH_REQUIRE(B > 0 && T > 0 && n > 0 && H > 0, "attn_space: empty problem");
   HH_REQUIRE(cls_ws != nullptr, "attn_space: CLS workspace");
+  if (attn_space_tc_supported(n)) return attn_space_tc(qkv, out, B, T, n, H, cls_ws, stream);  // tcgen05 path
   const int mblocks = (n + 15) / 16, kblocks = (n + 63) / 64;
   const size_t smem = static_cast<size_t>(mblocks * 16 + 16 + 2 * kblocks * 64) * LDS * sizeof(bf16) + 2 * HD * sizeof(float);
   HH_REQUIRE(smem <= 227 * 1024, "attn_space: patches per frame too large for the resident-K/V kernel");

@@ -80,6 +80,9 @@ int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, con
 size_t attn_cls_workspace_bytes(int B, int T, int n, int H);
 int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
 int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
+// tcgen05/TMEM implementation of attn_space for n <= 256 (attn_space dispatches to it; HH_ATTN_SPACE_MMA_SYNC=1 disables)
+bool attn_space_tc_supported(int n);
+int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
 int attn_cls_merge(const bf16* qkv, const float* parts, bf16* out, int B, int N, int H, int nparts, cudaStream_t stream);
 // Stand-alone CLS query row (reference statement of the fused path; used when T > 16).
 int attn_cls(const bf16* qkv, bf16* out, int B, int N, int H, cudaStream_t stream);
