@@ -202,3 +202,57 @@ def test_cpu_input_fails_loudly():
     video, _ = gc.make_inputs(case)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         clip.visual.forward_features(video)
+
+
+@pytest.mark.parametrize("T,nq,traj", [(4, 4, True), (16, 12, False)])
+def test_full_size_l14_against_oracle(T, nq, traj):
+    """BASELINE configs c1 / c2 geometry at full depth and width (TimeSformer-L/14, 24 blocks, 1024 wide; decoder
+    512 x 6 layers, 22 048 classes), one clip, against the fp32 oracle: the gates BASELINE.json states."""
+    LaviLa, D, metric = _mods()
+    from helping_hand_for_egocentric_videos_b200 import synthetic
+    vis = LaviLa.SpaceTimeTransformer(img_size=224, patch_size=14, embed_dim=1024, depth=24, num_heads=16, num_frames=T,
+                                      time_init='zeros', ln_pre=True, act_layer=LaviLa.QuickGELU, num_classes=0)
+    tr = D.Cross_Attention(normalize_before=True, return_intermediate_dec=True)
+    dec = D.ObjDecoder(tr, num_classes=22047, num_queries=nq + 1, aux_loss=True, pred_traj=traj, feature_dim=1024,
+                       num_frames=T, patches_per_frame=256)
+    synthetic.randomize_(vis, 5)
+    synthetic.randomize_(dec, 6)
+    vsd = {k: v.detach().clone() for k, v in vis.state_dict().items()}
+    dsd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    vis, dec = vis.cuda().eval(), dec.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    video = torch.randn(1, T, 3, 224, 224, generator=g)
+    text = torch.randn(5, 256, generator=g)
+    _, fmap = vis.forward_features(video.cuda())
+    out, hs, _, _ = dec(fmap[:, 1:].unflatten(1, (T, 256)))
+    emb = dec.obj_proj(hs[-1])                      # [1, Q, 256]: hand / object / video query embeddings
+    sim = metric.sim_matrix(text.cuda(), emb[0])
+    with torch.no_grad():
+        _, rfmap = O.encoder_forward(video, vsd, 16)
+        rout, rhs, _, _ = O.decoder_forward(rfmap[:, 1:].unflatten(1, (T, 256)), dsd, heads=8, pred_traj=traj)
+        remb = O.obj_proj(rhs[-1], dsd)
+        rsim = O.sim_matrix(text, remb[0])
+    cos_f = _cos(fmap.cpu(), rfmap)
+    cos_e = F.cosine_similarity(emb.cpu()[0], remb[0], dim=-1).min().item()
+    box = (out["pred_boxes"].cpu() - rout["pred_boxes"]).abs().max().item()
+    serr = (sim.cpu() - rsim).abs().max().item()
+    print("L/14 T=%d: fmap cos %.6f, embed cos %.6f, box L1 %.2e, sim err %.2e" % (T, cos_f, cos_e, box, serr))
+    assert cos_f >= 0.999 and cos_e >= 0.999
+    assert box <= 1e-2
+    assert out["pred_logits"].shape == rout["pred_logits"].shape and out["pred_boxes"].shape == rout["pred_boxes"].shape
+    assert serr <= 1e-2
+
+
+def test_noun_and_box_indices_exact():
+    """'box / noun index outputs exact' (SURVEY section 8a rows a17, a19): scipy's Hungarian assignment on costs built by
+    our kernels equals the assignment on the oracle's costs -- noun matching uses -cos(noun, query) (model/loss.py:88-92)."""
+    from scipy.optimize import linear_sum_assignment
+    _, _, metric = _mods()
+    g = torch.Generator().manual_seed(9)
+    for trial in range(16):
+        k = int(torch.randint(1, 5, (1,), generator=g))
+        nouns = torch.randn(k, 256, generator=g)
+        queries = torch.randn(12, 256, generator=g)
+        mine = linear_sum_assignment((-metric.sim_matrix(nouns.cuda(), queries.cuda())).cpu().numpy())
+        ref = linear_sum_assignment((-O.sim_matrix(nouns, queries)).numpy())
+        assert (mine[1] == ref[1]).all()
