@@ -162,7 +162,31 @@ def _group_mask(T: int, n: int, mode: str) -> Tensor:
 
 
 def var_attention(z: Tensor, w_qkv, b_qkv, w_proj, b_proj, heads: int, T: int, n: int, mode: str) -> Tensor:
-    """VarAttention.forward (model/LaviLa.py:246-283) as masked dense attention."""
+    """VarAttention.forward (model/LaviLa.py:246-283), grouped form: O(N (n + T)) like the reference, so that timing
+    this oracle is a fair stand-in for the reference's CPU cost.  Checked against `var_attention_masked` in the tests."""
+    B, N, D = z.shape
+    hd = D // heads
+    qkv = F.linear(z, w_qkv, b_qkv).view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)      # [3,B,H,N,hd]
+    q, k, v = qkv[0] * (hd ** -0.5), qkv[1], qkv[2]                                        # :249-252
+    # CLS query: all 1 + T*n keys (:258)
+    o_cls = torch.softmax(q[:, :, :1] @ k.transpose(-1, -2), dim=-1) @ v                   # [B,H,1,hd]
+    # patch queries: {CLS key} U own group (:260-270)
+    qp, kp, vp = (t[:, :, 1:].reshape(B, heads, T, n, hd) for t in (q, k, v))
+    if mode == "time":          # group = same patch position over frames: put p before f
+        qp, kp, vp = (t.transpose(2, 3) for t in (qp, kp, vp))                             # [B,H,n,T,hd]
+    s_grp = qp @ kp.transpose(-1, -2)                                                      # [B,H,G,L,L]
+    s_cls = (qp * k[:, :, :1, None]).sum(-1, keepdim=True)                                 # [B,H,G,L,1]
+    p = torch.softmax(torch.cat([s_cls, s_grp], dim=-1), dim=-1)
+    o = p[..., :1] * v[:, :, :1, None] + p[..., 1:] @ vp                                   # [B,H,G,L,hd]
+    if mode == "time":
+        o = o.transpose(2, 3)
+    o = torch.cat([o_cls, o.reshape(B, heads, T * n, hd)], dim=2)                          # :276
+    o = o.permute(0, 2, 1, 3).reshape(B, N, D)
+    return F.linear(o, w_proj, b_proj)                                                     # :281
+
+
+def var_attention_masked(z: Tensor, w_qkv, b_qkv, w_proj, b_proj, heads: int, T: int, n: int, mode: str) -> Tensor:
+    """The same operator as masked dense attention (independent second statement, O(N^2))."""
     B, N, D = z.shape
     hd = D // heads
     qkv = F.linear(z, w_qkv, b_qkv).view(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)

@@ -53,3 +53,20 @@ def test_group_mask_semantics():
     assert m[7].nonzero().flatten().tolist() == [0, 3, 7, 11]
     s = O._group_mask(T=3, n=4, mode="space")
     assert s[7].nonzero().flatten().tolist() == [0, 5, 6, 7, 8]
+
+
+def test_grouped_and_masked_attention_statements_agree():
+    """The oracle's O(N(n+T)) grouped attention equals its masked dense second statement."""
+    from oracle import hh_oracle as O
+    g = torch.Generator().manual_seed(3)
+    for (B, T, n, H) in [(2, 3, 5, 2), (1, 4, 16, 3), (1, 1, 7, 1)]:
+        D = H * 64
+        z = torch.randn(B, 1 + T * n, D, generator=g)
+        wq = torch.randn(3 * D, D, generator=g) / D ** 0.5
+        bq = torch.randn(3 * D, generator=g) * 0.1
+        wp = torch.randn(D, D, generator=g) / D ** 0.5
+        bp = torch.randn(D, generator=g) * 0.1
+        for mode in ("time", "space"):
+            a = O.var_attention(z, wq, bq, wp, bp, H, T, n, mode)
+            b = O.var_attention_masked(z, wq, bq, wp, bp, H, T, n, mode)
+            assert torch.allclose(a, b, atol=2e-5), (B, T, n, H, mode, (a - b).abs().max())
