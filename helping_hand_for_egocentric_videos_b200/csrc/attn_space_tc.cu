@@ -270,51 +270,83 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 
       mbar_wait(&ex->s_full[hf], tp);
       tc_fence_after();
-      // ---- pass 1: row maximum over the n patch keys and the CLS key
+      const int nch = (p.n + 31) >> 5;   // 32-key chunks that hold valid keys
+      // ---- pass 1: row maximum over the n patch keys and the CLS key.  TMEM loads are double-buffered (the load of
+      //      chunk c+1 is in flight while chunk c is reduced); 3-input FMNMX3 halves the instruction count.
       float mx = s_cls;
-#pragma unroll 1
-      for (int c = 0; c < ROWS / 32; ++c) {
-        if (c * 32 >= p.n) break;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_lane + c * 32, v);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= p.n) {
+      {
+        uint32_t va[32], vb[32];
+        auto reduce = [&](const uint32_t (&v)[32], int c) {
+          if (c * 32 + 32 <= p.n) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        } else {
+            for (int j = 0; j < 32; j += 2)
+              asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < p.n) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < p.n) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        };
+        tmem_ld_32x32b_x32(t_lane, va);
+#pragma unroll
+        for (int c = 0; c < ROWS / 32; c += 2) {
+          if (c < nch) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, vb);
+            reduce(va, c);
+          }
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld_32x32b_x32(t_lane + (c + 2) * 32, va);
+            reduce(vb, c + 1);
+          }
         }
       }
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
-      float l = p_cls;
-      // ---- pass 2: P = exp2(S - max) as bf16 pairs, written back over the S columns (16 columns per 32 keys)
-#pragma unroll 1
-      for (int c = 0; c < ROWS / 32; ++c) {
-        uint32_t w[16];
-        if (c * 32 < p.n) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_lane + c * 32, v);
-          tmem_ld_wait();
+      // ---- pass 2: P = exp2(S - max) as bf16 pairs, written back over the S columns (16 columns per 32 keys).
+      //      Packed FFMA2 / FADD2 for the scale-and-shift and the row sum; the exponentials are the MUFU floor.
+      float2 l2 = make_float2(p_cls, 0.f);
+      {
+        uint32_t va[32], vb[32];
+        const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
+        auto emit = [&](const uint32_t (&v)[32], int c) {
+          uint32_t w[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), LOG2E, -ml));
-            float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), LOG2E, -ml));
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
+            float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
             if (c * 32 + 32 > p.n) {  // ragged last chunk (n = 196)
-              if (c * 32 + j >= p.n) p0 = 0.f;
-              if (c * 32 + j + 1 >= p.n) p1 = 0.f;
+              if (c * 32 + j >= p.n) e.x = 0.f;
+              if (c * 32 + j + 1 >= p.n) e.y = 0.f;
             }
-            l += p0 + p1;
-            w[j >> 1] = pack_bf16x2(p0, p1);
+            l2 = __fadd2_rn(l2, e);
+            w[j >> 1] = pack_bf16x2(e.x, e.y);
           }
-        } else {
+          tmem_st_32x32b_x16(t_lane + c * 16, w);
+        };
+        tmem_ld_32x32b_x32(t_lane, va);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = 0u;
+        for (int c = 0; c < ROWS / 32; c += 2) {
+          if (c < nch) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, vb);
+            emit(va, c);
+          }
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld_32x32b_x32(t_lane + (c + 2) * 32, va);
+            emit(vb, c + 1);
+          }
         }
-        tmem_st_32x32b_x16(t_lane + c * 16, w);
+        if (nch < ROWS / 32) {  // key chunks past n: P = 0 (V rows there are zero-filled by TMA as well)
+          uint32_t z[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) z[j] = 0u;
+          for (int c = nch; c < ROWS / 32; ++c) tmem_st_32x32b_x16(t_lane + c * 16, z);
+        }
       }
+      const float l = l2.x + l2.y;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

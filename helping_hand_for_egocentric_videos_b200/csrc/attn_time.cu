@@ -11,6 +11,8 @@
 //   only live row is q_cls: each warp keeps a running (max, sum, o[64]) over the keys it sees and writes ONE partial
 //   per (clip, head, patch-chunk); attn_cls_merge folds the partials and the CLS key itself into output row 0.
 // attn_time (16 < T <= 32) keeps the simple SIMT kernel + the stand-alone CLS kernel.
+#include <cstdlib>
+
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
 
@@ -473,6 +475,12 @@ int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls
     HH_REQUIRE(cls_ws != nullptr, "attn_time: CLS workspace");
     const int pchunk = 16;
     const int nchunks = (n + pchunk - 1) / pchunk;
+    static const bool use_v1 = std::getenv("HH_ATTN_TIME_V1") != nullptr;
+    if (!use_v1) {  // double-buffered, swizzled-tile generation of the same kernel (attn_time_v2.cu)
+      int rc = attn_time_v2(qkv, out, B, T, n, H, cls_ws, pchunk, nchunks, stream);
+      if (rc) return rc;
+      return attn_cls_merge(qkv, cls_ws, out, B, 1 + T * n, H, nchunks, stream);
+    }
     const size_t smem = static_cast<size_t>(TW) * TWARP_ELEMS * sizeof(bf16);
     static bool configured = false;
     if (!configured) {

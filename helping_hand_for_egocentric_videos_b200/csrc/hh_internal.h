@@ -81,6 +81,8 @@ size_t attn_cls_workspace_bytes(int B, int T, int n, int H);
 int attn_space(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
 int attn_time(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
 // tcgen05/TMEM implementation of attn_space for n <= 256 (attn_space dispatches to it; HH_ATTN_SPACE_MMA_SYNC=1 disables)
+int attn_time_v2(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, int pchunk, int nchunks,
+                 cudaStream_t stream);
 bool attn_space_tc_supported(int n);
 int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, cudaStream_t stream);
 int attn_cls_merge(const bf16* qkv, const float* parts, bf16* out, int B, int N, int H, int nparts, cudaStream_t stream);
