@@ -5,14 +5,22 @@
 // One task = one (clip, frame, head): Q, K, V tiles of [n x 64] bf16.  All n keys fit one accumulator tile, so the
 // softmax is a single exact pass (no online rescaling):
 //     S[256 x 256] = Q K^T     2 halves of 128 rows: tcgen05.mma 128x256x16, A = Q (smem), B = K (smem), D -> TMEM
-//     P = exp2(S - max)        one thread per row reads its TMEM lane, writes P back as bf16 over the S columns
+//     P = exp2(S - max)        written back to TMEM as bf16 over the S columns
 //     O[256 x 64]  = P V       tcgen05.mma 128x64x16, A = P (TMEM), B = V (smem, N-major), D -> TMEM
 // plus the CLS key/value (one extra logit per row, folded in registers).
 //
-// Persistent CTA, 12 warps:  0 TMA producer (4-D tensor maps: rows past n are zero-filled / clipped by hardware, two
-// tasks in flight)  |  1 MMA issuer  |  2-3 CLS *query* partial over this frame's keys (SIMT; merged across frames by
-// attn_cls_merge)  |  4-7 softmax + epilogue of rows 0..127  |  8-11 the same for rows 128..255.
-// TMEM (512 columns): half h owns columns [256h, 256h+256): S, then P in the first 128 and O in the next 64.
+// Persistent CTA, 24 warps:
+//    0      TMA producer (4-D tensor maps: rows past n are zero-filled / clipped by hardware; the next task's tiles are
+//           in flight into the other smem stage while this one is processed)
+//    1      MMA issuer (one thread);  2  TMEM allocator
+//    4-19   softmax + epilogue: TMEM lane r = query row r of a half; the 256 key columns of a row are split between
+//           two threads (column groups A: keys 0..127, B: keys 128..255) that exchange their partial max / sum through
+//           shared memory -- 16 warps keep the MUFU and issue slots busy
+//    20-23  legacy-MMA helpers (highest warp ids = highest issue priority, they gate the softmax warps): the CLS-key
+//           logit of every row (q_r . k_cls) and the CLS *query*'s partial softmax over this frame's keys (merged
+//           across frames by attn_cls_merge)
+// TMEM (512 columns), half h owns [256h, 256h+256): S; then P_A in [0,64), P_B in [128,192), O in [192,256).
+#include <cstdio>
 #include <cstdlib>
 
 #include "hh_internal.h"
@@ -27,7 +35,7 @@ constexpr int ROWS = 256;                 // query / key slots per task
 constexpr int TILE_BYTES = ROWS * 128;    // 32 KB: [256 rows x 64 bf16], SWIZZLE_128B
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int NSTAGE = 2;
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 768;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int PART = HD + 2;
 
@@ -35,8 +43,11 @@ struct SmemExtras {
   __nv_bfloat16 cls_q[NSTAGE][HD];   // q, k, v of the CLS token for (clip, head) of the staged task
   __nv_bfloat16 cls_k[NSTAGE][HD];
   __nv_bfloat16 cls_v[NSTAGE][HD];
-  float merge[PART];                 // CLS-query partial of warp 3, folded by warp 2
-  uint64_t full[NSTAGE], empty[NSTAGE];
+  float scls[NSTAGE][ROWS];          // CLS-key logit of every query row
+  float xm[2][2][128];               // [half][column group][row]: partial row max
+  float xl[2][2][128];               // partial row sum
+  float merge[4][PART];              // CLS-query partials of the four helper warps
+  uint64_t full[NSTAGE], empty[NSTAGE], scls_full[NSTAGE];
   uint64_t s_full[2], p_full[2], o_full[2], t_free[2];
   uint32_t tmem_slot;
 };
@@ -46,20 +57,23 @@ struct TcArgs {
   const bf16* qkv;
   float* cls_part;
   int B, T, n, H;
+  unsigned long long* trace;   // debug: [role][task][event] %globaltimer stamps of CTA 0 (nullptr = off)
 };
 
-__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
+constexpr int TR_TASKS = 8, TR_EVENTS = 8, TR_ROLES = 6;
+__device__ __forceinline__ void trace_ev(const TcArgs& p, int role, int it, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < TR_TASKS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(role * TR_TASKS + it) * TR_EVENTS + ev] = t;
+  }
 }
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t sw128(uint32_t tile, int row, int chunk) {
+  return tile + static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -81,13 +95,14 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&ex->full[s], 1);
-      mbar_init(&ex->empty[s], 10);  // MMA commit + 8 epilogue warps (store has read its smem) + CLS-query warps
+      mbar_init(&ex->empty[s], 18);  // MMA commit + 16 epilogue warps (stores have read smem) + helper warps
+      mbar_init(&ex->scls_full[s], 4);
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&ex->s_full[h], 1);
-      mbar_init(&ex->p_full[h], 4);
+      mbar_init(&ex->p_full[h], 8);
       mbar_init(&ex->o_full[h], 1);
-      mbar_init(&ex->t_free[h], 4);
+      mbar_init(&ex->t_free[h], 8);
     }
     fence_mbar_init();
   }
@@ -109,10 +124,11 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const uint32_t ph = (it >> 1) & 1;
         const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
         mbar_wait(&ex->empty[st], ph ^ 1u);
+        trace_ev(p, 0, it, 0);
         uint8_t* base = smem + st * STAGE_BYTES;
         mbar_arrive_expect_tx(&ex->full[st], STAGE_BYTES + 3 * HD * 2);
-        tma_load_4d(&tm_in, &ex->full[st], base, h * HD, 0, f, b);                       // Q
-        tma_load_4d(&tm_in, &ex->full[st], base + TILE_BYTES, D + h * HD, 0, f, b);      // K
+        tma_load_4d(&tm_in, &ex->full[st], base, h * HD, 0, f, b);                           // Q
+        tma_load_4d(&tm_in, &ex->full[st], base + TILE_BYTES, D + h * HD, 0, f, b);          // K
         tma_load_4d(&tm_in, &ex->full[st], base + 2 * TILE_BYTES, 2 * D + h * HD, 0, f, b);  // V
         const bf16* cls = p.qkv + static_cast<size_t>(b) * N * 3 * D + h * HD;
         bulk_load_1d(ex->cls_q[st], cls, HD * 2, &ex->full[st]);
@@ -121,7 +137,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
+    // ================================================================== MMA issuer (one thread)
+    // Both 128-row halves of a task run concurrently on the two TMEM halves; the next task's Q/K/V are already in
+    // flight into the other smem stage.
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, HD);
@@ -133,6 +151,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
         const uint32_t ks = qs + TILE_BYTES, vs = qs + 2 * TILE_BYTES;
         mbar_wait(&ex->full[st], ph);
+        trace_ev(p, 1, it, 0);
         tc_fence_after();
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&ex->t_free[hf], tp ^ 1u);   // previous task's O has left these columns
@@ -143,236 +162,316 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           for (int k = 0; k < HD / 16; ++k)
             umma_bf16(tmem_base + hf * 256, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&ex->s_full[hf]);
+          trace_ev(p, 1, it, 1 + hf);
         }
         for (int hf = 0; hf < 2; ++hf) {
           mbar_wait(&ex->p_full[hf], tp);
+          trace_ev(p, 1, it, 3 + 2 * hf);
           tc_fence_after();
           const uint64_t dv = umma_desc_sw128_mn(vs);
 #pragma unroll
-          for (int k = 0; k < ROWS / 16; ++k)   // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
-            umma_bf16_ts(tmem_base + hf * 256 + 128, tmem_base + hf * 256 + 8 * k, dv + static_cast<uint64_t>(k * 128),
+          for (int k = 0; k < ROWS / 16; ++k) {  // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
+            const uint32_t pcol = (k < 8) ? 8 * k : 128 + 8 * (k - 8);
+            umma_bf16_ts(tmem_base + hf * 256 + 192, tmem_base + hf * 256 + pcol, dv + static_cast<uint64_t>(k * 128),
                          idesc_o, k > 0 ? 1u : 0u);
+          }
           umma_commit(&ex->o_full[hf]);
+          trace_ev(p, 1, it, 4 + 2 * hf);
         }
         umma_commit(&ex->empty[st]);  // every MMA that read this stage's Q, K, V has retired
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ================================================================== CLS-query partial (SIMT, 64 threads)
-    const int ww = warp - 2;
+  } else if (warp >= 20) {
+    // ================================================================== helpers on the legacy tensor-core path
+    // 4 warps; every warp takes 4 of the 16 query-row blocks for the CLS-key logits and 64 of the 256 keys for the
+    // CLS-query partial.  Fragment loads are issued in batches ahead of the MMAs that use them (one warp has no other
+    // warp to hide its ldmatrix -> mma latency behind).
+    const int ww = warp - 20;
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = lane >> 3, lr = lane & 7;
     int it = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
       mbar_wait(&ex->full[st], ph);
-      const uint32_t ks = smem_u32(smem + st * STAGE_BYTES + TILE_BYTES);
-      const uint32_t vs = ks + TILE_BYTES;
-      float q[HD];
+      if (ww == 0 && lane == 0) trace_ev(p, 2, it, 0);
+      const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
+      const uint32_t ks = qs + TILE_BYTES, vs = ks + TILE_BYTES;
+
+      // ---- (1) CLS-key logit of every query row: S_cls = Q . k_cls, as m16n8k16 with k_cls in column 0 of B
+      uint32_t kb0[4], kb1[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = *reinterpret_cast<const uint4*>(&ex->cls_q[st][c * 8]);
-        float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), dd = unpack_bf16x2(u.w);
-        q[c * 8 + 0] = a.x; q[c * 8 + 1] = a.y; q[c * 8 + 2] = bb.x; q[c * 8 + 3] = bb.y;
-        q[c * 8 + 4] = cc.x; q[c * 8 + 5] = cc.y; q[c * 8 + 6] = dd.x; q[c * 8 + 7] = dd.y;
+      for (int kk = 0; kk < 4; ++kk) {
+        kb0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[st][kk * 16 + 2 * t]) : 0u;
+        kb1[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[st][kk * 16 + 8 + 2 * t]) : 0u;
       }
-      // phase A: lane <-> key (4 keys per lane of this warp's 128-key half)
-      float s[4];
-      float m = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = ww * 128 + i * 32 + lane;
-        float acc = 0.f;
+      for (int half = 0; half < 2; ++half) {   // 2 x 2 row blocks; 8 fragment loads in flight
+        uint32_t qf[2][4][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = ld_shared_v4(ks + j * 128 + ((c ^ (j & 7)) << 4));
-          float2 a = unpack_bf16x2(u.x), bb = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), dd = unpack_bf16x2(u.w);
-          acc += q[c * 8 + 0] * a.x + q[c * 8 + 1] * a.y + q[c * 8 + 2] * bb.x + q[c * 8 + 3] * bb.y +
-                 q[c * 8 + 4] * cc.x + q[c * 8 + 5] * cc.y + q[c * 8 + 6] * dd.x + q[c * 8 + 7] * dd.y;
-        }
-        s[i] = (j < p.n) ? acc : -INFINITY;
-        m = fmaxf(m, s[i]);
-      }
-      m = warp_max(m);
-      float l = 0.f;
-      const float ml = (m == -INFINITY) ? 0.f : m * LOG2E;
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], LOG2E, -ml));   // -inf -> 0
-        l += s[i];
-      }
-      l = warp_sum(l);
-      // phase B: lane <-> output dims (2*lane, 2*lane+1)
-      float o0 = 0.f, o1 = 0.f;
+          for (int kk = 0; kk < 4; ++kk)
+            ldsm_x4(qf[i][kk], sw128(qs, (ww * 4 + half * 2 + i) * 16 + (mi & 1) * 8 + lr, kk * 2 + (mi >> 1)));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll 8
-        for (int sl = 0; sl < 32; ++sl) {
-          const float pj = __shfl_sync(0xffffffffu, s[i], sl);
-          const int j = ww * 128 + i * 32 + sl;
-          const float2 v = unpack_bf16x2(ld_shared_u32(vs + j * 128 + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4));
-          o0 = fmaf(pj, v.x, o0);
-          o1 = fmaf(pj, v.y, o1);
+        for (int i = 0; i < 2; ++i) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(acc, qf[i][kk], kb0[kk], kb1[kk]);
+          if (t == 0) {  // column 0 of the 16x8 result: rows g and g+8
+            const int mb = ww * 4 + half * 2 + i;
+            ex->scls[st][mb * 16 + g] = acc[0];
+            ex->scls[st][mb * 16 + g + 8] = acc[2];
+          }
         }
       }
-      if (ww == 1) {
-        if (lane == 0) {
-          ex->merge[0] = m;
-          ex->merge[1] = l;
-        }
-        ex->merge[2 + 2 * lane] = o0;
-        ex->merge[2 + 2 * lane + 1] = o1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ex->scls_full[st]);
+      if (ww == 0 && lane == 0) trace_ev(p, 2, it, 1);
+
+      // ---- (2) CLS query vs this warp's 64 keys: online softmax over 2 blocks of 32 keys, row 0 of the A block live
+      uint32_t qa0[4], qa2[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        qa0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[st][kk * 16 + 2 * t]) : 0u;
+        qa2[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[st][kk * 16 + 8 + 2 * t]) : 0u;
       }
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      if (ww == 0) {
-        const float m1 = ex->merge[0], l1 = ex->merge[1];
-        const float mm = fmaxf(m, m1);
-        const float c0 = (m == -INFINITY) ? 0.f : fast_exp2((m - mm) * LOG2E);
-        const float c1 = (m1 == -INFINITY) ? 0.f : fast_exp2((m1 - mm) * LOG2E);
+      float m = -INFINITY, l = 0.f;
+      float o[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) o[ni][0] = o[ni][1] = o[ni][2] = o[ni][3] = 0.f;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        const int key0 = ww * 64 + blk * 32;
+        if (key0 >= p.n) break;
+        uint32_t kf[8][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int np = 0; np < 2; ++np)
+            ldsm_x4(kf[kk * 2 + np], sw128(ks, key0 + np * 16 + (mi >> 1) * 8 + lr, kk * 2 + (mi & 1)));
+        float s[4][4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t qf[4] = {qa0[kk], 0u, qa2[kk], 0u};
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {
+            mma_bf16_16816(s[2 * np], qf, kf[kk * 2 + np][0], kf[kk * 2 + np][1]);
+            mma_bf16_16816(s[2 * np + 1], qf, kf[kk * 2 + np][2], kf[kk * 2 + np][3]);
+          }
+        }
+        uint32_t vf[8][4];   // V fragments of this block: in flight during the softmax arithmetic
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp)
+            ldsm_x4_trans(vf[kk * 4 + dp], sw128(vs, key0 + kk * 16 + (mi & 1) * 8 + lr, dp * 2 + (mi >> 1)));
+        float mx = -INFINITY;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int key = key0 + ni * 8 + 2 * t;
+          if (key >= p.n) s[ni][0] = -INFINITY;
+          if (key + 1 >= p.n) s[ni][1] = -INFINITY;
+          mx = fmaxf(mx, fmaxf(s[ni][0], s[ni][1]));
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m, mx);       // finite: key0 < n
+        const float corr = fast_exp2((m - mn) * LOG2E);
+        m = mn;
+        l *= corr;
+        uint32_t pa[2][4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const float p0 = fast_exp2(fmaf(s[ni][0], LOG2E, -mn * LOG2E)), p1 = fast_exp2(fmaf(s[ni][1], LOG2E, -mn * LOG2E));
+          l += p0 + p1;
+          pa[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+          pa[ni >> 1][(ni & 1) * 2 + 1] = 0u;
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          o[ni][0] *= corr;
+          o[ni][1] *= corr;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            mma_bf16_16816(o[2 * dp], pa[kk], vf[kk * 4 + dp][0], vf[kk * 4 + dp][1]);
+            mma_bf16_16816(o[2 * dp + 1], pa[kk], vf[kk * 4 + dp][2], vf[kk * 4 + dp][3]);
+          }
+        }
+      }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      // row 0 lives in lanes 0..3 (g == 0): the four warps' partials are folded by warp 4 and written to [b][h][f]
+      if (g == 0) {
+        float* mg = ex->merge[ww];
+        if (t == 0) {
+          mg[0] = m;
+          mg[1] = l;
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          mg[2 + ni * 8 + 2 * t] = o[ni][0];
+          mg[2 + ni * 8 + 2 * t + 1] = o[ni][1];
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (ww == 0 && g == 0) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) mm = fmaxf(mm, ex->merge[w][0]);
+        float cw[4], ll = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          cw[w] = (ex->merge[w][0] == -INFINITY) ? 0.f : fast_exp2((ex->merge[w][0] - mm) * LOG2E);
+          ll += ex->merge[w][1] * cw[w];
+        }
         float* dst = p.cls_part + ((static_cast<size_t>(b) * p.H + h) * p.T + f) * PART;
-        if (lane == 0) {
+        if (t == 0) {
           dst[0] = mm;
-          dst[1] = l * c0 + l1 * c1;
+          dst[1] = ll;
         }
-        dst[2 + 2 * lane] = o0 * c0 + ex->merge[2 + 2 * lane] * c1;
-        dst[2 + 2 * lane + 1] = o1 * c0 + ex->merge[2 + 2 * lane + 1] * c1;
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int idx = 2 + ni * 8 + 2 * t + e;
+            dst[idx] = ex->merge[0][idx] * cw[0] + ex->merge[1][idx] * cw[1] + ex->merge[2][idx] * cw[2] +
+                       ex->merge[3][idx] * cw[3];
+          }
+        }
       }
-      asm volatile("bar.sync 2, 64;" ::: "memory");  // merge[] reusable; both warps are done with K and V
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // merge[] reusable; all four warps are done with Q, K and V
       if (ww == 0 && lane == 0) mbar_arrive(&ex->empty[st]);
+      if (ww == 0 && lane == 0) trace_ev(p, 2, it, 2);
     }
-  } else {
-    // ================================================================== softmax + epilogue (one thread per row)
-    const int hf = (warp - 4) >> 2;           // 0: rows 0..127, 1: rows 128..255
+  } else if (warp >= 4) {
+    // ================================================================== softmax + epilogue (two threads per row)
+    const int sw = warp - 4;                  // 0..15
+    const int hf = (sw >> 2) & 1;             // 0: rows 0..127, 1: rows 128..255 (TMEM half hf)
+    const int cg = sw >> 3;                   // column group: 0 = keys 0..127, 1 = keys 128..255
     const int wq = warp & 3;                  // TMEM lane quarter of this warp
-    const int r = hf * 128 + wq * 32 + lane;  // row within the task
+    const int rl = wq * 32 + lane;            // row within the half
+    const int r = hf * 128 + rl;              // row within the task
+    const int jh = hf;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(hf * 256);
-    const uint32_t sw = static_cast<uint32_t>(r & 7);
-    int it = 0;
-    for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++it) {
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      const uint32_t tp = it & 1;
+    const uint32_t s_col = t_lane + cg * 128;               // this thread's 128 S columns
+    const uint32_t p_col = t_lane + (cg ? 128 : 0);         // its 64 P columns
+    const uint32_t o_col = t_lane + 192 + cg * 32;          // its 32 O columns (dims cg*32 ..)
+    const int key_base = cg * 128;
+    const int bar_id = 3 + hf;                              // named barrier of the 256 threads of this half
+    const int nvalid = min(128, max(0, p.n - key_base));    // valid keys in this thread's column group
+    const int nch = (nvalid + 31) >> 5;
+    int u = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++u) {
+      const int st = u & 1;
+      const uint32_t ph = (u >> 1) & 1;
+      const uint32_t tp = u & 1;
       const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
-      mbar_wait(&ex->full[st], ph);
-
-      // ---- logit of the CLS key for this row: q_r . k_cls
-      float s_cls = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = ld_shared_v4(qs + r * 128 + ((static_cast<uint32_t>(c) ^ sw) << 4));
-        const uint4 kk = *reinterpret_cast<const uint4*>(&ex->cls_k[st][c * 8]);
-        const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-        const float2 k0 = unpack_bf16x2(kk.x), k1 = unpack_bf16x2(kk.y), k2 = unpack_bf16x2(kk.z), k3 = unpack_bf16x2(kk.w);
-        s_cls += a0.x * k0.x + a0.y * k0.y + a1.x * k1.x + a1.y * k1.y + a2.x * k2.x + a2.y * k2.y + a3.x * k3.x +
-                 a3.y * k3.y;
-      }
-
+      mbar_wait(&ex->full[st], ph);        // TMA-written cls_v visible to this thread
+      mbar_wait(&ex->scls_full[st], ph);
+     {
+      const float s_cls = ex->scls[st][r];
+      const bool tr = (cg == 0 && wq == 0 && lane == 0);
       mbar_wait(&ex->s_full[hf], tp);
+      if (tr) trace_ev(p, 3 + jh, u, 0);
       tc_fence_after();
-      const int nch = (p.n + 31) >> 5;   // 32-key chunks that hold valid keys
-      // ---- pass 1: row maximum over the n patch keys and the CLS key.  TMEM loads are double-buffered (the load of
-      //      chunk c+1 is in flight while chunk c is reduced); 3-input FMNMX3 halves the instruction count.
+
+      // ---- pass 1: partial row maximum over this thread's keys
       float mx = s_cls;
-      {
-        uint32_t va[32], vb[32];
-        auto reduce = [&](const uint32_t (&v)[32], int c) {
-          if (c * 32 + 32 <= p.n) {
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(s_col + c * 32, v);
+        tmem_ld_wait();
+        if (c * 32 + 32 <= nvalid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-              asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
-          } else {
+          for (int j = 0; j < 32; j += 2)
+            asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < p.n) mx = fmaxf(mx, __uint_as_float(v[j]));
-          }
-        };
-        tmem_ld_32x32b_x32(t_lane, va);
-#pragma unroll
-        for (int c = 0; c < ROWS / 32; c += 2) {
-          if (c < nch) {
-            tmem_ld_wait();
-            if (c + 1 < nch) tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, vb);
-            reduce(va, c);
-          }
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld_32x32b_x32(t_lane + (c + 2) * 32, va);
-            reduce(vb, c + 1);
-          }
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
       }
+      ex->xm[hf][cg][rl] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, ex->xm[hf][cg ^ 1][rl]);
+      if (tr) trace_ev(p, 3 + jh, u, 1);
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
-      // ---- pass 2: P = exp2(S - max) as bf16 pairs, written back over the S columns (16 columns per 32 keys).
-      //      Packed FFMA2 / FADD2 for the scale-and-shift and the row sum; the exponentials are the MUFU floor.
-      float2 l2 = make_float2(p_cls, 0.f);
+
+      // ---- pass 2: P = exp2(S - max) as bf16 pairs into this group's P columns (16 columns per 32 keys)
+      float2 l2 = make_float2(0.f, 0.f);
       {
-        uint32_t va[32], vb[32];
         const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
-        auto emit = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
           uint32_t w[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-            float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-            if (c * 32 + 32 > p.n) {  // ragged last chunk (n = 196)
-              if (c * 32 + j >= p.n) e.x = 0.f;
-              if (c * 32 + j + 1 >= p.n) e.y = 0.f;
-            }
-            l2 = __fadd2_rn(l2, e);
-            w[j >> 1] = pack_bf16x2(e.x, e.y);
-          }
-          tmem_st_32x32b_x16(t_lane + c * 16, w);
-        };
-        tmem_ld_32x32b_x32(t_lane, va);
-#pragma unroll
-        for (int c = 0; c < ROWS / 32; c += 2) {
           if (c < nch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(s_col + c * 32, v);
             tmem_ld_wait();
-            if (c + 1 < nch) tmem_ld_32x32b_x32(t_lane + (c + 1) * 32, vb);
-            emit(va, c);
-          }
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld_32x32b_x32(t_lane + (c + 2) * 32, va);
-            emit(vb, c + 1);
-          }
-        }
-        if (nch < ROWS / 32) {  // key chunks past n: P = 0 (V rows there are zero-filled by TMA as well)
-          uint32_t z[16];
+            if (c * 32 + 32 <= nvalid) {   // full chunk: no per-element masking code at all
 #pragma unroll
-          for (int j = 0; j < 16; ++j) z[j] = 0u;
-          for (int c = nch; c < ROWS / 32; ++c) tmem_st_32x32b_x16(t_lane + c * 16, z);
+              for (int j = 0; j < 32; j += 2) {
+                const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
+                const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+                l2 = __fadd2_rn(l2, e);
+                w[j >> 1] = pack_bf16x2(e.x, e.y);
+              }
+            } else {                       // ragged last chunk (n = 196)
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
+                float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+                if (c * 32 + j >= nvalid) e.x = 0.f;
+                if (c * 32 + j + 1 >= nvalid) e.y = 0.f;
+                l2 = __fadd2_rn(l2, e);
+                w[j >> 1] = pack_bf16x2(e.x, e.y);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = 0u;
+          }
+          tmem_st_32x32b_x16(p_col + c * 16, w);
         }
       }
-      const float l = l2.x + l2.y;
+      ex->xl[hf][cg][rl] = l2.x + l2.y;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->p_full[hf]);
+      if (tr) trace_ev(p, 3 + jh, u, 2);
 
-      // ---- O = P V is in TMEM columns [128, 192) of this half
+      // ---- O = P V is in TMEM columns [192, 256) of this half; this thread takes 32 of the 64 output dims
       mbar_wait(&ex->o_full[hf], tp);
+      if (tr) trace_ev(p, 3 + jh, u, 3);
       tc_fence_after();
-      uint32_t o[64];
-      {
-        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
-        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[32]);
-        tmem_ld_32x32b_x32(t_lane + 128, lo);
-        tmem_ld_32x32b_x32(t_lane + 160, hi);
-        tmem_ld_wait();
-      }
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_col, o);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->t_free[hf]);   // the next task's S may overwrite this half
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // both groups' xl are visible
+      const float l = ex->xl[hf][0][rl] + ex->xl[hf][1][rl] + p_cls;
 
-      // ---- normalise (+ CLS value), stage bf16 row into the (consumed) Q tile, bulk-store 32-row boxes
+      // ---- normalise (+ CLS value), stage the 32 bf16 values (64 B) of this row, bulk-store a 32-row x 64-B box
       const float inv = 1.f / l;
       const float pc = p_cls * inv;
+      // staging: the 4 KB of the (consumed) Q tile that belong to these 32 rows, 2 KB per column group, SWIZZLE_64B
+      const uint32_t stg = qs + static_cast<uint32_t>((jh * 128 + wq * 32) * 128 + cg * 2048);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[st][c * 8]);
+      for (int c = 0; c < 4; ++c) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[st][cg * 32 + c * 8]);
         const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z), v3 = unpack_bf16x2(vv.w);
         const uint32_t w0 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 0]), inv, pc * v0.x),
                                         fmaf(__uint_as_float(o[c * 8 + 1]), inv, pc * v0.y));
@@ -382,20 +481,22 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                                         fmaf(__uint_as_float(o[c * 8 + 5]), inv, pc * v2.y));
         const uint32_t w3 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 6]), inv, pc * v3.x),
                                         fmaf(__uint_as_float(o[c * 8 + 7]), inv, pc * v3.y));
-        st_shared_v4(qs + r * 128 + ((static_cast<uint32_t>(c) ^ sw) << 4), w0, w1, w2, w3);
+        st_shared_v4(stg + static_cast<uint32_t>(lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)), w0, w1, w2, w3);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        const int row0 = hf * 128 + wq * 32;
+        const int row0 = jh * 128 + wq * 32;
         if (row0 < p.n) {
-          tma_store_4d(&tm_out, qs + row0 * 128, h * HD, row0, f, b);
+          tma_store_4d(&tm_out, stg, h * HD + cg * 32, row0, f, b);
           tma_store_commit();
-          tma_store_wait_read<0>();
         }
+        tma_store_wait_read<0>();   // the store has read its staging rows: this warp is done with the stage
         mbar_arrive(&ex->empty[st]);
       }
       __syncwarp();
+      if (tr) trace_ev(p, 3 + jh, u, 4);
+     }
     }
   }
 
@@ -424,17 +525,18 @@ EncodeTiledFn encode_fn() {
 }
 
 // [cols, n, T, B] view of a token matrix whose rows are (clip, 1 + frame*n + patch): skips the CLS row of each clip.
-int make_map4d(CUtensorMap* map, const bf16* base_row1, int cols, int n, int T, int B, int N, int box_rows) {
+int make_map4d(CUtensorMap* map, const bf16* base_row1, int cols, int n, int T, int B, int N, int box_cols, int box_rows,
+               CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(T),
                         static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(n) * cols * 2,
                         static_cast<cuuint64_t>(N) * cols * 2};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base_row1), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled (4-D) failed with CUresult " + std::to_string((int)r));
   return 0;
@@ -454,9 +556,9 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
              "attn_space_tc: 16-byte alignment");
   const int D = H * HD, N = 1 + T * n;
   CUtensorMap tm_in, tm_out;
-  int rc = make_map4d(&tm_in, qkv + static_cast<size_t>(3) * D, 3 * D, n, T, B, N, ROWS);
+  int rc = make_map4d(&tm_in, qkv + static_cast<size_t>(3) * D, 3 * D, n, T, B, N, 64, ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_map4d(&tm_out, out + D, D, n, T, B, N, 32);
+  rc = make_map4d(&tm_out, out + D, D, n, T, B, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -470,11 +572,37 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
   a.T = T;
   a.n = n;
   a.H = H;
+  a.trace = nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  static const bool want_trace = std::getenv("HH_ATTN_TRACE") != nullptr;
+  if (want_trace) {
+    if (!trace_buf) HH_CHECK_CUDA(cudaMalloc(&trace_buf, sizeof(unsigned long long) * TR_ROLES * TR_TASKS * TR_EVENTS));
+    HH_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * TR_ROLES * TR_TASKS * TR_EVENTS, stream));
+    a.trace = trace_buf;
+  }
   const int ntasks = B * T * H;
   int grid = num_sms();
   if (grid > ntasks) grid = ntasks;
   attn_space_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tm_in, tm_out, a);
   HH_CHECK_LAUNCH("attn_space_tc_kernel");
+  if (want_trace) {  // debug only: dump the timeline of CTA 0 (ns relative to the first stamp)
+    static unsigned long long host[TR_ROLES * TR_TASKS * TR_EVENTS];
+    HH_CHECK_CUDA(cudaStreamSynchronize(stream));
+    HH_CHECK_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (unsigned long long v : host) if (v && v < t0) t0 = v;
+    const char* names[TR_ROLES] = {"producer", "mma", "helper", "softmax.h0", "softmax.h1", "-"};
+    for (int r = 0; r < TR_ROLES - 1; ++r)
+      for (int t = 0; t < TR_TASKS; ++t) {
+        std::string line = std::string(names[r]) + " task " + std::to_string(t) + ":";
+        bool any = false;
+        for (int e = 0; e < TR_EVENTS; ++e) {
+          const unsigned long long v = host[(r * TR_TASKS + t) * TR_EVENTS + e];
+          if (v) { any = true; line += " e" + std::to_string(e) + "=" + std::to_string((long long)(v - t0)); }
+        }
+        if (any) fprintf(stderr, "[attn trace] %s\n", line.c_str());
+      }
+  }
   return attn_cls_merge(qkv, cls_ws, out, B, N, H, T, stream);
 }
 
