@@ -303,6 +303,17 @@ def main():
     for k in gemm_flops:
         if k in prof and prof[k][0] > 0:
             per_class[k]["tflops"] = gemm_flops[k] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12
+    # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture at these very shapes
+    # (profiles/r1_gemm_traffic.json), averaged over the launches of one step like `achieved`.
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.isfile(tpath) and B == 64 and T == 16:
+        with open(tpath) as f:
+            tk = json.load(f)["kernels"]
+        per_step = {"qkv": 48, "proj": 48, "fc1": 24, "fc2": 24}
+        traffic = {"avg_dram_bytes_per_launch": sum(tk[k]["dram_bytes_per_launch"] * c for k, c in per_step.items()) / 144,
+                   "avg_algorithmic_bytes_per_launch": sum(tk[k]["algorithmic_bytes"] * c for k, c in per_step.items()) / 144,
+                   "source": "profiles/r1_gemm_ncu_full.md"}
     path_tflops = value / world * flops_clip / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -318,7 +329,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05, encoder qkv/proj/fc1/fc2 launches)",
                      "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["sustained"], "peak_source": peaks["source"] + " sustained bf16",
-                     "share_of_step": g_ms / args.steps / ms_step if ms_step > 0 else None, "traffic": None},
+                     "share_of_step": g_ms / args.steps / ms_step if ms_step > 0 else None, "traffic": traffic},
         "clocks": clocks, "gpu_launches": launches_step * args.steps,
     }
     if e2e:
