@@ -24,6 +24,10 @@ class DecoderCfg(C.Structure):
                                        "num_classes1", "feature_dim", "num_frames", "patches_per_frame", "pred_traj")]
 
 
+class TextCfg(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("vocab_size", "context_length", "width", "heads", "layers", "embed_dim")]
+
+
 _p, _i, _f, _i64, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/hh_b200.h declares (tests/test_capi_symbols.py checks)
@@ -43,6 +47,13 @@ SIGNATURES = {
     "hh_decoder_forward": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
     "hh_decoder_flops_per_clip": (C.c_double, [_p, _i]),
     "hh_decoder_last_launches": (_i, [_p]),
+    "hh_text_create": (_i, [C.POINTER(_p), C.POINTER(TextCfg)]),
+    "hh_text_destroy": (None, [_p]),
+    "hh_text_set_weight": (_i, [_p, C.c_char_p, _p, _i64, _p]),
+    "hh_text_forward": (_i, [_p, _p, _i, _p, _p, _p]),
+    "hh_text_flops_per_sequence": (C.c_double, [_p]),
+    "hh_text_last_launches": (_i, [_p]),
+    "hh_attention_causal": (_i, [_p, _p, _i, _i, _i, _p]),
     "hh_profile_num_classes": (_i, []),
     "hh_profile_class_name": (C.c_char_p, [_i]),
     "hh_encoder_set_profile": (_i, [_p, _i]),

@@ -18,6 +18,11 @@ struct hh_decoder {
   explicit hh_decoder(const hh_decoder_cfg& c) : impl(c) {}
 };
 
+struct hh_text {
+  TextEncoder impl;
+  explicit hh_text(const hh_text_cfg& c) : impl(c) {}
+};
+
 #define HH_GUARD_BEGIN try {
 #define HH_GUARD_END                                              \
   }                                                               \
@@ -89,6 +94,33 @@ int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b,
 }
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T) { return dec ? dec->impl.flops_per_clip(T) : 0.0; }
 int hh_decoder_last_launches(const hh_decoder* dec) { return dec ? dec->impl.launches : 0; }
+
+// ------------------------------------------------------------------------------------------ text tower
+int hh_text_create(hh_text** out, const hh_text_cfg* cfg) {
+  HH_GUARD_BEGIN
+  if (!out || !cfg) return fail(-2, "hh_text_create: null argument");
+  int rc = TextEncoder::validate(*cfg);
+  if (rc) return rc;
+  *out = new hh_text(*cfg);
+  return 0;
+  HH_GUARD_END
+}
+void hh_text_destroy(hh_text* txt) { delete txt; }
+int hh_text_set_weight(hh_text* txt, const char* key, const float* data, int64_t numel, void* stream) {
+  HH_GUARD_BEGIN
+  if (!txt) return fail(-1, "hh_text_set_weight: null handle");
+  if (!key || !data) return fail(-2, "hh_text_set_weight: null argument");
+  return txt->impl.weights.set(key, data, numel, S(stream));
+  HH_GUARD_END
+}
+int hh_text_forward(hh_text* txt, const int64_t* tokens, int G, float* embed, float* fmap, void* stream) {
+  HH_GUARD_BEGIN
+  if (!txt) return fail(-1, "hh_text_forward: null handle");
+  return txt->impl.forward(tokens, G, embed, fmap, S(stream));
+  HH_GUARD_END
+}
+double hh_text_flops_per_sequence(const hh_text* txt) { return txt ? txt->impl.flops_per_sequence() : 0.0; }
+int hh_text_last_launches(const hh_text* txt) { return txt ? txt->impl.launches : 0; }
 
 // ------------------------------------------------------------------------------------------ event profiler
 static const char* kClassNames[K_NUM] = {"gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_patch", "layernorm",
@@ -193,6 +225,10 @@ int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, f
   return cross_attn(q, static_cast<const bf16*>(K), static_cast<const bf16*>(V), ldkv, out, B, Q, heads, S_, ws.ptr,
                     S(stream));
   HH_GUARD_END
+}
+
+int hh_attention_causal(const void* qkv, void* out, int G, int L, int H, void* stream) {
+  return attn_causal(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), G, L, H, S(stream));
 }
 
 int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,

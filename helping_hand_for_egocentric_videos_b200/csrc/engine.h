@@ -88,4 +88,25 @@ struct Decoder {
   double flops_per_clip(int T) const;
 };
 
+// CLIP text tower (text.cu): CLIP.encode_text, model/LaviLa.py:660-670.
+struct TextEncoder {
+  hh_text_cfg cfg;
+  int max_chunk = 1024;  // sequences per pass through the workspace
+  int launches = 0;
+  WeightStore weights;
+  struct Layer {
+    DevBuf w_qkv, b_qkv, w_proj, w_fc1, w_fc2;
+  };
+  std::vector<Layer> layers;
+  DevBuf w_projT, flag;
+  DevBuf ws_x, ws_dl, ws_a, ws_qkv, ws_h, ws_out, ws_cls;
+
+  explicit TextEncoder(const hh_text_cfg& c);
+  static int validate(const hh_text_cfg& c);
+  int pack(cudaStream_t s);
+  // tokens int64 [G, L] -> embed fp32 [G, E] (x[eot] @ text_projection, may be null), fmap fp32 [G, L, W] (may be null)
+  int forward(const int64_t* tokens, int G, float* embed, float* fmap, cudaStream_t s);
+  double flops_per_sequence() const;
+};
+
 }  // namespace hh

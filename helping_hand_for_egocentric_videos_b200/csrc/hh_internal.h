@@ -89,6 +89,9 @@ int attn_cls_merge(const bf16* qkv, const float* parts, bf16* out, int B, int N,
 // Stand-alone CLS query row (reference statement of the fused path; used when T > 16).
 int attn_cls(const bf16* qkv, bf16* out, int B, int N, int H, cudaStream_t stream);
 
+// Causal self-attention of the CLIP text tower (text.cu): qkv bf16 [G*L, 3*H*64] (q pre-scaled) -> out bf16 [G*L, H*64]
+int attn_causal(const bf16* qkv, bf16* out, int G, int L, int H, cudaStream_t stream);
+
 // ---------------------------------------------------------------- decoder satellites (decoder.cu)
 // Small-M fp32 linear: out[R,N] = act((in[R,K] (+ in_add[r % add_mod, K])) * W[N,K]^T + bias) (+ residual[R,N]).
 struct LinArgs {

@@ -9,8 +9,8 @@ module in place of the reference's:
 
 The nn.Module tree below only *holds parameters* (so load_state_dict / .to() / named_parameters() behave); the video
 forward (SpaceTimeTransformer.forward_features, reference model/LaviLa.py:537-573) is one call into the C ABI
-(hh_encoder_forward).  There is no PyTorch fallback for it.  The CLIP text tower (reference :660-670) is outside the
-accelerated path for now and runs as ordinary PyTorch modules with reference-identical keys.
+(hh_encoder_forward).  There is no PyTorch fallback for it.  The CLIP text tower (reference :660-670; SURVEY.md
+section 8f, row 1) is likewise one call (hh_text_forward) over parameter containers with reference-identical keys.
 """
 from __future__ import annotations
 
@@ -239,8 +239,11 @@ class SpaceTimeTransformer(nn.Module):
         return self.head(x_cls), x
 
 
-# ---------------------------------------------------------------------------------------------- text tower (PyTorch)
+# ---------------------------------------------------------------------------------------------- text tower
 class ResidualAttentionBlock(nn.Module):
+    """Parameter container with the keys of reference model/openai_model.py:182-216 (attn.in_proj_weight, ln_1, mlp.c_fc,
+    ...).  The arithmetic runs in the C engine (CLIP.encode_text)."""
+
     def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None):
         super().__init__()
         self.attn = nn.MultiheadAttention(d_model, n_head)
@@ -251,10 +254,7 @@ class ResidualAttentionBlock(nn.Module):
         self.attn_mask = attn_mask
 
     def forward(self, x: torch.Tensor, use_checkpoint=False):
-        m = self.attn_mask.to(dtype=x.dtype, device=x.device) if self.attn_mask is not None else None
-        y = self.ln_1(x)
-        x = x + self.attn(y, y, y, need_weights=False, attn_mask=m)[0]
-        return x + self.mlp(self.ln_2(x))
+        raise NotImplementedError("the text blocks run inside hh_text_forward; call CLIP.encode_text")
 
 
 class Transformer(nn.Module):
@@ -262,10 +262,11 @@ class Transformer(nn.Module):
         super().__init__()
         self.width = width
         self.layers = layers
+        self.heads = heads
         self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
 
     def forward(self, x: torch.Tensor, use_checkpoint=False):
-        return self.resblocks(x)
+        raise NotImplementedError("the text blocks run inside hh_text_forward; call CLIP.encode_text")
 
 
 class CLIP(nn.Module):
@@ -289,6 +290,10 @@ class CLIP(nn.Module):
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / tempearture_init))
         self.initialize_parameters()
         self._proj_t = None
+        self._text_cfg = L.TextCfg(vocab_size=vocab_size, context_length=context_length, width=transformer_width,
+                                   heads=transformer_heads, layers=transformer_layers, embed_dim=embed_dim)
+        self._text_handle = None
+        self._text_sync = _ParamSync()
 
     def initialize_parameters(self):
         nn.init.normal_(self.token_embedding.weight, std=0.02)
@@ -324,14 +329,56 @@ class CLIP(nn.Module):
         x_cls = ops.linear_f32(x_cls.contiguous(), self._image_projection_t())      # x_cls @ image_projection (:657)
         return x_cls, x
 
+    # -- text engine plumbing ----------------------------------------------------------------------------------
+    def _text_engine(self):
+        if self._text_handle is None:
+            h = C.c_void_p()
+            L.check(L.load().hh_text_create(C.byref(h), C.byref(self._text_cfg)), "hh_text_create")
+            self._text_handle = h
+        return self._text_handle
+
+    def __del__(self):
+        h = getattr(self, "_text_handle", None)
+        if h is not None and L._lib is not None:
+            L._lib.hh_text_destroy(h)
+            self._text_handle = None
+
+    def _text_params(self):
+        keep = ("transformer.", "token_embedding.", "positional_embedding", "ln_final.", "text_projection")
+        for k, p in self.named_parameters():
+            if k.startswith(keep):
+                yield k, p
+
+    def sync_text_weights(self):
+        h, lib = self._text_engine(), L.load()
+
+        def setter(key, src):
+            L.check(lib.hh_text_set_weight(h, key.encode(), L.ptr(src), src.numel(), L.stream_ptr()),
+                    "hh_text_set_weight(%s)" % key)
+        self._text_sync.sync(self._text_params(), setter)
+
+    def text_flops_per_sequence(self) -> float:
+        return L.load().hh_text_flops_per_sequence(self._text_engine())
+
+    @torch.no_grad()
     def encode_text(self, text, use_checkpoint=False):
-        x = self.token_embedding(text)
-        x = x + self.positional_embedding
-        x = x.permute(1, 0, 2)
-        x = self.transformer(x, use_checkpoint=use_checkpoint)
-        x = x.permute(1, 0, 2)
-        x = self.ln_final(x)
-        x_cls = x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ self.text_projection
+        """text int64 [G, context_length] -> (x_cls [G, embed_dim], x [G, context_length, width]); reference
+        model/LaviLa.py:660-670.  The tower is frozen in every reference script (run/train.py:88,109)."""
+        if not text.is_cuda:
+            raise RuntimeError("helping_hand_for_egocentric_videos_b200: the text tower runs on CUDA only "
+                               "(got a %s tensor); there is no CPU fallback" % text.device)
+        if text.dim() != 2 or text.shape[1] != self.context_length:
+            raise ValueError("text must be [G, %d] token ids, got %s" % (self.context_length, tuple(text.shape)))
+        if text.dtype not in (torch.int64, torch.int32):
+            raise TypeError("text must hold integer token ids, got %s" % text.dtype)
+        with torch.cuda.device(text.device):
+            self.sync_text_weights()
+            tok = text.to(torch.int64).contiguous()
+            G = tok.shape[0]
+            x_cls = torch.empty(G, self._text_cfg.embed_dim, device=text.device, dtype=torch.float32)
+            x = torch.empty(G, self.context_length, self._text_cfg.width, device=text.device, dtype=torch.float32)
+            L.check(L.load().hh_text_forward(self._text_engine(), L.ptr(tok), G, L.ptr(x_cls), L.ptr(x), L.stream_ptr()),
+                    "hh_text_forward")
         return x_cls, x
 
     def forward(self, image, text, use_checkpoint=False, norm_embed=True, return_feature_map=False):

@@ -65,6 +65,14 @@ def attention(qkv: torch.Tensor, B: int, T: int, n: int, H: int, standalone_cls:
     return outs
 
 
+def attention_causal(qkv: torch.Tensor, G: int, Lc: int, H: int) -> torch.Tensor:
+    """Causal self-attention of the text tower on packed qkv (bf16 [G*Lc, 3*H*64], q pre-scaled) -> bf16 [G*Lc, H*64]."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (G * Lc, 3 * H * 64)
+    o = torch.empty(G * Lc, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.load().hh_attention_causal(L.ptr(qkv), L.ptr(o), G, Lc, H, L.stream_ptr()), "hh_attention_causal")
+    return o
+
+
 def cross_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, B: int, Q: int, heads: int, S: int,
                     simt: bool = False) -> torch.Tensor:
     """q fp32 [B*Q, heads*64] (pre-scaled); K, V bf16 [B*S, heads*64].  `simt` selects the fp32 SIMT statement."""

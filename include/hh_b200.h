@@ -24,6 +24,7 @@ extern "C" {
 
 typedef struct hh_encoder hh_encoder;
 typedef struct hh_decoder hh_decoder;
+typedef struct hh_text hh_text;
 
 const char* hh_last_error(void);
 int hh_version(void);
@@ -91,6 +92,32 @@ int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b,
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
 int hh_decoder_last_launches(const hh_decoder* dec);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * CLIP text tower: CLIP.encode_text  (model/LaviLa.py:660-670) over ResidualAttentionBlock (model/openai_model.py:
+ * 182-216): token + positional embedding, `layers` pre-norm blocks with causal attention and QuickGELU MLP, ln_final,
+ * end-of-text row (argmax of the token ids) @ text_projection.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int vocab_size;      /* 49408 */
+  int context_length;  /* 77 */
+  int width;           /* 512 (BASE) / 768 (LARGE); heads of 64 */
+  int heads;
+  int layers;          /* 12 */
+  int embed_dim;       /* projection width, 256 */
+} hh_text_cfg;
+
+int hh_text_create(hh_text** out, const hh_text_cfg* cfg);
+void hh_text_destroy(hh_text* txt);
+/* `key`: CLIP state_dict key of the text side ("token_embedding.weight", "positional_embedding",
+ * "transformer.resblocks.3.attn.in_proj_weight", "ln_final.bias", "text_projection", ...). */
+int hh_text_set_weight(hh_text* txt, const char* key, const float* data, int64_t numel, void* stream);
+/* tokens int64 [G, context_length] (device) -> embed fp32 [G, embed_dim] (un-normalised x_cls, LaviLa.py:669) and
+ * fmap fp32 [G, context_length, width] (ln_final of every token, :667).  Either output may be NULL.  Synchronises the
+ * stream once to report token ids outside [0, vocab_size) (the reference's nn.Embedding device-asserts on those). */
+int hh_text_forward(hh_text* txt, const int64_t* tokens, int G, float* embed, float* fmap, void* stream);
+double hh_text_flops_per_sequence(const hh_text* txt);
+int hh_text_last_launches(const hh_text* txt);
+
 /* Per-kernel-class device timing (CUDA events recorded on the launching stream around every launch while enabled).
  * hh_*_profile waits for the recorded events, writes the summed milliseconds and launch counts of every class
  * (arrays of hh_profile_num_classes() entries) since the previous call, and resets the recorder. */
@@ -144,6 +171,8 @@ int hh_attention(const void* qkv, void* out, int B, int T, int n, int H, int kin
 /* Query->patch cross attention (tfm_decoder.py:438-441 core): q fp32 [B*Q, heads*64] pre-scaled, K/V bf16 [B*S, ldkv]. */
 int hh_cross_attention(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
                        int S, void* stream);
+/* Causal self-attention core of the text tower: qkv bf16 [G*L, 3*H*64] (q pre-scaled) -> out bf16 [G*L, H*64]. */
+int hh_attention_causal(const void* qkv, void* out, int G, int L, int H, void* stream);
 /* Same operator on the fp32 SIMT kernel (second implementation kept for differential testing). */
 int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
                             int S, void* stream);

@@ -136,6 +136,21 @@ def test_divided_attention(B, T, n, H):
         _close(outs[mode][cls_rows], ref[cls_rows], 2 ** -6, 1e-3, "CLS row %s" % mode)
 
 
+@pytest.mark.parametrize("G,Lc,H", [(3, 77, 8), (2, 77, 12), (5, 16, 2), (2, 33, 4), (1, 130, 2), (4, 1, 2)])
+def test_causal_attention(G, Lc, H):
+    """Text-tower attention core against dense masked softmax (nn.MultiheadAttention + triu(-inf) mask,
+    reference model/openai_model.py:199-201) on the same bf16-rounded, pre-scaled qkv."""
+    g = torch.Generator().manual_seed(G * 1000 + Lc)
+    qkv = (torch.randn(G * Lc, 3 * H * 64, generator=g) * 0.7)
+    qkv[:, :H * 64] *= 0.125
+    qkv = qkv.to(torch.bfloat16).cuda()
+    got = _ops().attention_causal(qkv, G, Lc, H)
+    x = qkv.float().view(G, Lc, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = x[0] @ x[1].transpose(-1, -2) + torch.full((Lc, Lc), float("-inf"), device="cuda").triu_(1)
+    ref = (torch.softmax(s, -1) @ x[2]).permute(0, 2, 1, 3).reshape(G * Lc, H * 64)
+    _close(got, ref, 2 ** -6, 6e-3, "causal attention")
+
+
 @pytest.mark.parametrize("B,Q,heads,S", [(2, 5, 2, 48), (1, 13, 8, 4096), (3, 13, 8, 784), (2, 16, 1, 100), (1, 1, 2, 31)])
 def test_cross_attention(B, Q, heads, S):
     ops = _ops()
