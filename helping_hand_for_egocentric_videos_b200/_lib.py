@@ -53,6 +53,15 @@ SIGNATURES = {
     "hh_text_forward": (_i, [_p, _p, _i, _p, _p, _p]),
     "hh_text_flops_per_sequence": (C.c_double, [_p]),
     "hh_text_last_launches": (_i, [_p]),
+    "hh_assign": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "hh_match_cost_class": (_i, [_p, _i, _i, _p, _i, _f, _p, _p]),
+    "hh_sim_matrix_backward_workspace_bytes": (_sz, [_i, _i]),
+    "hh_sim_matrix_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p]),
+    "hh_egonce_forward": (_i, [_p, _i, _i, _p, _p, _i, _p, _f, _f, _p, _p, _p, _p]),
+    "hh_egonce_backward": (_i, [_p, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
+    "hh_word_loss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "hh_word_loss_forward": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "hh_word_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hh_attention_causal": (_i, [_p, _p, _i, _i, _i, _p]),
     "hh_profile_num_classes": (_i, []),
     "hh_profile_class_name": (C.c_char_p, [_i]),

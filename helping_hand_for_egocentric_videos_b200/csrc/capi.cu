@@ -185,6 +185,50 @@ int hh_box_match_cost(const float* pred, const float* tgt, int N, int M, float w
   return box_match_cost(pred, tgt, N, M, w_bbox, w_giou, cost, S(stream));
 }
 
+int hh_assign(const float* cost, const int64_t* offset, const int32_t* ld, const int32_t* nr, const int32_t* nc,
+              const uint8_t* row_valid, int row_valid_ld, int P, int max_dim, int64_t* row_ind, int64_t* col_ind,
+              int32_t* count, int out_ld, void* stream) {
+  return assign_lsa(cost, reinterpret_cast<const long long*>(offset), ld, nr, nc, row_valid, row_valid_ld, P,
+                    max_dim, reinterpret_cast<long long*>(row_ind), reinterpret_cast<long long*>(col_ind), count, out_ld,
+                    S(stream));
+}
+int hh_match_cost_class(const float* logits, int N, int ncls, const int64_t* ids, int M, float w, float* cost,
+                        void* stream) {
+  return match_cost_class(logits, N, ncls, reinterpret_cast<const long long*>(ids), M, w, cost, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------ losses
+size_t hh_sim_matrix_backward_workspace_bytes(int Na, int Nb) { return sim_matrix_backward_workspace_bytes(Na, Nb); }
+int hh_sim_matrix_backward(const float* a, const float* b, const float* G, const float* gscale, float* da, float* db,
+                           int Na, int Nb, int d, float eps, void* workspace, void* stream) {
+  return sim_matrix_backward(a, b, G, gscale, da, db, Na, Nb, d, eps, workspace, S(stream));
+}
+int hh_egonce_forward(const float* x, int N, int M, const float* mask_v, const float* mask_n, int R, const float* pad,
+                      float temperature, float vn_threshold, uint8_t* mask_bool, uint8_t* keep, float* saved,
+                      void* stream) {
+  return egonce_forward(x, N, M, mask_v, mask_n, R, pad, temperature, vn_threshold, mask_bool, keep, saved, S(stream));
+}
+int hh_egonce_backward(const float* x, int N, int M, float temperature, const uint8_t* mask_bool, const uint8_t* keep,
+                       const float* saved, const float* grad_loss, float* grad_x, void* stream) {
+  return egonce_backward(x, N, M, temperature, mask_bool, keep, saved, grad_loss, grad_x, S(stream));
+}
+size_t hh_word_loss_workspace_bytes(int V, int d, int B2, int Q, int Wm) {
+  return word_loss_workspace_bytes(V, d, B2, Q, Wm);
+}
+int hh_word_loss_forward(const float* noun_embeds, int V, int d, const float* pred, int B2, int Q,
+                         const int64_t* gt_inds, int Wm, float temperature, float noun_threshold, int64_t* col_ind,
+                         float* sel, int64_t* sel_row, float* dlogits, float* stats, void* workspace, void* stream) {
+  return word_loss_forward(noun_embeds, V, d, pred, B2, Q, reinterpret_cast<const long long*>(gt_inds), Wm, temperature,
+                           noun_threshold, reinterpret_cast<long long*>(col_ind), sel,
+                           reinterpret_cast<long long*>(sel_row), dlogits, stats, workspace, S(stream));
+}
+int hh_word_loss_backward(const float* noun_embeds, int V, int d, int B2, int Q, int Wm, const float* sel,
+                          const int64_t* sel_row, const float* dlogits, float* stats, const float* grad_loss,
+                          float* d_pred, float* d_nouns, void* workspace, void* stream) {
+  return word_loss_backward(noun_embeds, V, d, B2, Q, Wm, sel, reinterpret_cast<const long long*>(sel_row), dlogits,
+                            stats, grad_loss, d_pred, d_nouns, workspace, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------ kernel-level entry points
 int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
                  const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream) {

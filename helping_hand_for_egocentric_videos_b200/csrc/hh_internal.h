@@ -146,4 +146,37 @@ int box_pairwise(const float* b1, const float* b2, int N, int M, float* iou, flo
 int box_match_cost(const float* pred, const float* tgt, int N, int M, float w_bbox, float w_giou, float* cost,
                    cudaStream_t stream);
 
+
+// ---------------------------------------------------------------- assignment (assign.cu)
+// P independent rectangular linear-sum-assignment problems (scipy.optimize.linear_sum_assignment semantics and index
+// order).  Problem p: rows nr[p] (optionally filtered by row_valid[p, :]), columns nc[p], entry (i,j) at
+// cost[offset[p] + i*ld[p] + j].  Outputs padded with -1; count[p] = pairs found, -1 if infeasible / oversized.
+int assign_lsa(const float* cost, const long long* offset, const int* ld, const int* nr, const int* nc,
+               const unsigned char* row_valid, int row_valid_ld, int P, int max_dim, long long* row_ind,
+               long long* col_ind, int* count, int out_ld, cudaStream_t stream);
+// cost[r, t] += w * -softmax(logits[r, :ncls])[ids[t]]   (matcher class term, model/box_utils.py:66,83-85)
+int match_cost_class(const float* logits, int N, int ncls, const long long* ids, int M, float w, float* cost,
+                     cudaStream_t stream);
+
+// ---------------------------------------------------------------- losses (loss.cu)
+// Gradient of sim_matrix(a, b) (eps-clamped cosine): G [Na, Nb] (scaled by *gscale when given) -> da [Na,d], db [Nb,d]
+// (either may be null).
+size_t sim_matrix_backward_workspace_bytes(int Na, int Nb);
+int sim_matrix_backward(const float* a, const float* b, const float* G, const float* gscale, float* da, float* db, int Na,
+                        int Nb, int d, float eps, void* workspace, cudaStream_t s);
+// EgoNCE (model/loss.py:15-70).  saved: fp32 [3N + 3M + 2]; saved[3N + 3M] = loss, [3N + 3M + 1] = kept rows.
+int egonce_forward(const float* x, int N, int M, const float* mask_v, const float* mask_n, int R, const float* pad,
+                   float temperature, float vn_threshold, unsigned char* mask_bool, unsigned char* keep, float* saved,
+                   cudaStream_t s);
+int egonce_backward(const float* x, int N, int M, float temperature, const unsigned char* mask_bool,
+                    const unsigned char* keep, const float* saved, const float* grad_loss, float* grad_x, cudaStream_t s);
+// WordContrastiveLoss (model/loss.py:78-106).  stats fp32 [4]: loss, matched nouns, 1/matched, scratch.
+size_t word_loss_workspace_bytes(int V, int d, int B2, int Q, int Wm);
+int word_loss_forward(const float* nouns, int V, int d, const float* pred, int B2, int Q, const long long* gt_inds, int Wm,
+                      float temperature, float noun_threshold, long long* col_ind, float* sel, long long* sel_row,
+                      float* dlogits, float* stats, void* workspace, cudaStream_t s);
+int word_loss_backward(const float* nouns, int V, int d, int B2, int Q, int Wm, const float* sel, const long long* sel_row,
+                       const float* dlogits, const float* stats, const float* grad_loss, float* d_pred, float* d_nouns,
+                       void* workspace, cudaStream_t s);
+
 }  // namespace hh

@@ -7,11 +7,31 @@ import torch
 from .. import ops
 
 
+class _SimMatrixFn(torch.autograd.Function):
+    """sim_matrix with its backward kernel (hh_sim_matrix_backward), for the training-side callers
+    (reference run/train.py:136, model/loss.py:96)."""
+
+    @staticmethod
+    def forward(ctx, a, b, eps):
+        ctx.save_for_backward(a, b)
+        ctx.eps = eps
+        return ops.sim_matrix(a, b, eps)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, b = ctx.saved_tensors
+        da, db = ops.sim_matrix_backward(a, b, grad.contiguous(), ctx.eps, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[1])
+        return da, db, None
+
+
 def sim_matrix(a, b, eps=1e-8, norm=True):
     """L2-normalise (norms clamped at eps) + similarity in one kernel.  2-D inputs -> mm, 3-D -> bmm, as the reference."""
     if not norm:
         raise NotImplementedError("sim_matrix(norm=False) is never used by the reference scripts")
     if a.dim() == 2:
+        if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+            return _SimMatrixFn.apply(a.float().contiguous(), b.float().contiguous(), eps)
         return ops.sim_matrix(a, b, eps)
     if a.dim() == 3:
         return torch.stack([ops.sim_matrix(x, y, eps) for x, y in zip(a, b)])

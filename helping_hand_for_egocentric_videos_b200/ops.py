@@ -165,3 +165,63 @@ def box_match_cost(pred: torch.Tensor, tgt: torch.Tensor, w_bbox: float = 5.0, w
         L.check(L.load().hh_box_match_cost(L.ptr(pred), L.ptr(tgt), N, M, w_bbox, w_giou, L.ptr(cost), L.stream_ptr()),
                 "hh_box_match_cost")
     return cost
+
+
+def match_cost_class(cost: torch.Tensor, logits: torch.Tensor, tgt_ids: torch.Tensor, weight: float) -> torch.Tensor:
+    """cost[r, t] += weight * -softmax(logits[r])[tgt_ids[t]] in place (matcher class term, reference
+    model/box_utils.py:66,83-85)."""
+    logits = _f32(logits)
+    ids = tgt_ids.to(torch.int64).contiguous()
+    N, M = cost.shape
+    assert logits.shape[0] == N and ids.numel() == M and cost.dtype == torch.float32 and cost.is_contiguous()
+    if N > 0 and M > 0:
+        L.check(L.load().hh_match_cost_class(L.ptr(logits), N, logits.shape[1], L.ptr(ids), M, float(weight), L.ptr(cost),
+                                             L.stream_ptr()), "hh_match_cost_class")
+    return cost
+
+
+def assign(cost: torch.Tensor, offset, ld, nr, nc, row_valid: torch.Tensor | None = None):
+    """Batched exact linear-sum assignment on the device (scipy.optimize.linear_sum_assignment semantics / index order).
+    Problem p = the nr[p] x nc[p] block of the fp32 tensor `cost` starting at element offset[p] with row stride ld[p];
+    `row_valid` (uint8/bool [P, max nr]) drops rows first.  offset/ld/nr/nc are host sequences.
+    Returns (row_ind int64 [P, K], col_ind int64 [P, K], count int32 [P]) on the device, -1 padded."""
+    P = len(nr)
+    assert cost.dtype == torch.float32 and cost.is_contiguous() and cost.is_cuda
+    max_dim = max([1] + [int(v) for v in nr] + [int(v) for v in nc])
+    if max_dim > 32:
+        raise NotImplementedError("assignment problems larger than 32 x 32 are not supported (got %d)" % max_dim)
+    K = max(1, min(max([0] + [int(v) for v in nr]), max([0] + [int(v) for v in nc])))
+    dev = cost.device
+    ri = torch.full((P, K), -1, dtype=torch.int64, device=dev)
+    ci = torch.full((P, K), -1, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(P, dtype=torch.int32, device=dev)
+    if P == 0:
+        return ri, ci, cnt
+    meta64 = torch.tensor([int(v) for v in offset], dtype=torch.int64).to(dev, non_blocking=True)
+    meta32 = torch.tensor([[int(v) for v in ld], [int(v) for v in nr], [int(v) for v in nc]],
+                          dtype=torch.int32).to(dev, non_blocking=True)
+    rv, rv_ld = None, 0
+    if row_valid is not None:
+        rv = row_valid.to(torch.uint8).contiguous()
+        assert rv.shape[0] == P
+        rv_ld = rv.shape[1]
+    L.check(L.load().hh_assign(L.ptr(cost), L.ptr(meta64), L.ptr(meta32[0]), L.ptr(meta32[1]), L.ptr(meta32[2]),
+                               L.ptr(rv), rv_ld, P, max_dim, L.ptr(ri), L.ptr(ci), L.ptr(cnt), K, L.stream_ptr()),
+            "hh_assign")
+    return ri, ci, cnt
+
+
+def sim_matrix_backward(a: torch.Tensor, b: torch.Tensor, grad: torch.Tensor, eps: float = 1e-8, need_a: bool = True,
+                        need_b: bool = True):
+    """Gradient of sim_matrix(a, b) w.r.t. a and b (None where not needed)."""
+    a, b, grad = _f32(a), _f32(b), _f32(grad)
+    Na, d = a.shape
+    Nb = b.shape[0]
+    assert grad.shape == (Na, Nb)
+    lib = L.load()
+    ws = torch.empty(lib.hh_sim_matrix_backward_workspace_bytes(Na, Nb), dtype=torch.uint8, device=a.device)
+    da = torch.empty_like(a) if need_a else None
+    db = torch.empty_like(b) if need_b else None
+    L.check(lib.hh_sim_matrix_backward(L.ptr(a), L.ptr(b), L.ptr(grad), None, L.ptr(da), L.ptr(db), Na, Nb, d, eps,
+                                       L.ptr(ws), L.stream_ptr()), "hh_sim_matrix_backward")
+    return da, db

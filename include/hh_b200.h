@@ -178,6 +178,56 @@ int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ld
                             int S, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Assignment: the per-image / per-clip scipy.optimize.linear_sum_assignment calls of HungarianMatcher.forward
+ * (model/box_utils.py:89-92) and WordContrastiveLoss.forward (model/loss.py:88-93), batched on the device.
+ * Problem p has nr[p] rows (only those with row_valid[p*row_valid_ld + r] != 0 when row_valid is given; the kept rows
+ * are renumbered 0..) and nc[p] columns (each <= max_dim <= 32); entry (i, j) = cost[offset[p] + i*ld[p] + j].
+ * row_ind / col_ind [P, out_ld] int64 receive the pairs in scipy's order (ascending row), -1 padded;
+ * count[p] = number of pairs (min(rows, cols)), or -1 when the problem is infeasible (inf / nan) or oversized.
+ * All arrays are device memory.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int hh_assign(const float* cost, const int64_t* offset, const int32_t* ld, const int32_t* nr, const int32_t* nc,
+              const uint8_t* row_valid, int row_valid_ld, int P, int max_dim, int64_t* row_ind, int64_t* col_ind,
+              int32_t* count, int out_ld, void* stream);
+/* cost[r, t] += w * -softmax(logits[r, :])[ids[t]]  for r < N, t < M: the classification term of the matcher cost
+ * (model/box_utils.py:66,83-85; only evaluated when exclude_class=False). */
+int hh_match_cost_class(const float* logits, int N, int ncls, const int64_t* ids, int M, float w, float* cost,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-side scoring losses (forward + backward).  All buffers are device memory owned by the caller.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* Gradient of hh_sim_matrix: G fp32 [Na, Nb] (multiplied by *gscale when gscale != NULL) -> da [Na, d], db [Nb, d]
+ * (either may be NULL).  workspace: hh_sim_matrix_backward_workspace_bytes(Na, Nb) bytes. */
+size_t hh_sim_matrix_backward_workspace_bytes(int Na, int Nb);
+int hh_sim_matrix_backward(const float* a, const float* b, const float* G, const float* gscale, float* da, float* db,
+                           int Na, int Nb, int d, float eps, void* workspace, void* stream);
+/* EgoNCE.forward (model/loss.py:15-70).  x fp32 [N, M] similarities, N = R * M (R captions per video, video-major);
+ * mask_v / mask_n fp32 [M, M] (either may be NULL); pad fp32 [N, M] or NULL (single-positive branch, R = 1).
+ * Outputs: mask_bool uint8 [N, M] (before the padded rows are dropped), keep uint8 [N] (row survives
+ * `masked_x.sum(-1) != -inf`), saved fp32 [3N + 3M + 2] (row/column log-sum-exp, positive counts, per-row/column terms;
+ * saved[3N + 3M] = loss, saved[3N + 3M + 1] = number of kept rows). */
+int hh_egonce_forward(const float* x, int N, int M, const float* mask_v, const float* mask_n, int R, const float* pad,
+                      float temperature, float vn_threshold, uint8_t* mask_bool, uint8_t* keep, float* saved,
+                      void* stream);
+/* grad_x [N, M] = d loss / d x * (*grad_loss); rows dropped by `keep` get 0. */
+int hh_egonce_backward(const float* x, int N, int M, float temperature, const uint8_t* mask_bool, const uint8_t* keep,
+                       const float* saved, const float* grad_loss, float* grad_x, void* stream);
+/* WordContrastiveLoss.forward (model/loss.py:78-106).  noun_embeds fp32 [V, d]; pred fp32 [B2, Q, d] (object-query
+ * embeddings); gt_inds int64 [B2, Wm] (0 = no noun).  Outputs: col_ind int64 [B2, Wm] = query matched to each noun slot
+ * (-1 for empty slots; the k-th non-empty slot of a clip carries scipy's col_ind[k]), sel fp32 [B2*Wm, d] (matched query
+ * rows), sel_row int64 [B2*Wm] (row of pred, -1 if empty), dlogits fp32 [B2*Wm, V] (d loss_slot / d similarity),
+ * stats fp32 [4] (stats[0] = loss, stats[1] = matched nouns).  A noun id outside [0, V) makes the loss NaN. */
+size_t hh_word_loss_workspace_bytes(int V, int d, int B2, int Q, int Wm);
+int hh_word_loss_forward(const float* noun_embeds, int V, int d, const float* pred, int B2, int Q,
+                         const int64_t* gt_inds, int Wm, float temperature, float noun_threshold, int64_t* col_ind,
+                         float* sel, int64_t* sel_row, float* dlogits, float* stats, void* workspace, void* stream);
+/* d_pred fp32 [B2*Q, d] and d_nouns fp32 [V, d] (either may be NULL), scaled by *grad_loss. */
+int hh_word_loss_backward(const float* noun_embeds, int V, int d, int B2, int Q, int Wm, const float* sel,
+                          const int64_t* sel_row, const float* dlogits, float* stats, const float* grad_loss,
+                          float* d_pred, float* d_nouns, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Data-parallel exchange: the one collective of the path (all-gather of embeddings for the cross-rank similarity
  * matrix, run/train.py:36-37,126-128; _valid_all_gather, utils/train_utils.py:51-59).  NCCL is resolved at run time
  * (dlopen of the libnccl.so.2 already loaded by the host framework); one communicator per process / GPU.

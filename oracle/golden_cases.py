@@ -33,6 +33,10 @@ CASES = {
                    logit_stride=37),
     "boxes": dict(kind="boxes", seed=31, N=40, M=7),
     "score": dict(kind="score", seed=41, Na=6, Nb=10, d=256, G=12),
+    # training-side rows a17-a19: matcher indices, EgoNCE (multi-positive, single-positive, noun-only), word loss,
+    # with the reference's own autograd gradients
+    "losses": dict(kind="losses", seed=51, Nv=6, R=5, d=32, V=50, B2=6, Q=12, Wm=4, bs=5, nq=10, ncls=20,
+                   sizes=(3, 0, 4, 1, 2)),
 }
 
 
@@ -81,6 +85,39 @@ def make_inputs(case):
         t[0] = p[3]            # identical pair: GIoU != 1 because of the +1e-4 (utils/box_ops.py:36)
         t[1, 2:] = 0.0         # degenerate (zero-area) target
         return p, t
+    if kind == "losses":
+        c = case
+        Nv, R, d = c["Nv"], c["R"], c["d"]
+        vid = torch.randn(Nv, d, generator=g)
+        txt = vid.repeat_interleave(R, 0) * 0.6 + torch.randn(Nv * R, d, generator=g)
+        verb = (torch.rand(Nv, 12, generator=g) < 0.25).float()
+        noun = (torch.rand(Nv, 20, generator=g) < 0.2).float()
+        verb[1] = verb[0]
+        noun[1] = noun[0]                      # videos 0/1 share verbs and nouns: extra positives
+        pad = (torch.rand(Nv * R, generator=g) > 0.3).float()
+        pad[::R] = 1.0                          # the original caption of every clip is never padding
+        pad = pad[:, None].repeat(1, Nv)
+        nouns = torch.randn(c["V"], d, generator=g)
+        nouns[7] = nouns[3] + 0.05 * torch.randn(d, generator=g)      # near-synonyms (cos > 0.6): masked logits
+        nouns[11] = nouns[3] + 0.3 * torch.randn(d, generator=g)
+        pred = torch.randn(c["B2"], c["Q"], d, generator=g)
+        inds = torch.randint(1, c["V"], (c["B2"], c["Wm"]), generator=g)
+        inds[0] = torch.tensor([3, 0, 7, 0])    # holes in the middle, synonyms as targets
+        inds[1] = 0                             # clip without nouns
+        inds[2, 1:] = 0
+        inds[3, 0] = 0
+        inds[4] = torch.tensor([11, 11, 3, 5])  # repeated noun
+        pred[4, 2] = pred[4, 9]                 # identical queries: tied assignment costs
+
+        def rb(k):
+            return torch.cat([0.2 + 0.6 * torch.rand(k, 2, generator=g), 0.02 + 0.35 * torch.rand(k, 2, generator=g)], -1)
+        pb = rb(c["bs"] * c["nq"]).view(c["bs"], c["nq"], 4)
+        pb[2, 4] = pb[2, 1]                     # duplicate predictions: tied matcher costs
+        pl = torch.randn(c["bs"], c["nq"], c["ncls"], generator=g)
+        tb = [rb(k) for k in c["sizes"]]
+        tl = [torch.randint(0, c["ncls"], (k,), generator=g) for k in c["sizes"]]
+        return dict(vid=vid, txt=txt, verb=verb, noun=noun, pad=pad, nouns=nouns, pred=pred, inds=inds, pred_boxes=pb,
+                    pred_logits=pl, tgt_boxes=tb, tgt_labels=tl)
     if kind == "score":
         a = torch.randn(case["Na"], case["d"], generator=g)
         b = torch.randn(case["Nb"], case["d"], generator=g)
@@ -91,6 +128,43 @@ def make_inputs(case):
         types = torch.randint(1, 3, (G,), generator=g)
         return a, b, preds, labels, types
     raise ValueError(kind)
+
+
+def run_losses(inp, sim_matrix, egonce, word_loss, matcher):
+    """Shared driver of the 'losses' case: the same sequence of calls is made with the reference's modules
+    (make_golden.py), the oracle's restatements (run_oracle) and the CUDA mirrors (tests/test_gpu_losses.py).
+    egonce(x, mask_v, mask_n, pad) -> (loss, mask_bool); word_loss(nouns, pred, inds) -> (loss, flat col indices);
+    matcher(outputs, targets, exclude_class) -> [(i, j)]."""
+    res = {}
+    vid = inp["vid"].clone().requires_grad_(True)
+    txt = inp["txt"].clone().requires_grad_(True)
+    sim_v, sim_n = sim_matrix(inp["verb"], inp["verb"]), sim_matrix(inp["noun"], inp["noun"])
+    x = sim_matrix(txt, vid)
+    res["x"] = x.detach()
+    loss, mb = egonce(x, sim_v, sim_n, inp["pad"])
+    loss.backward()
+    res.update(nce_multi=loss.detach(), nce_multi_mask=mb, nce_multi_dvid=vid.grad.clone(), nce_multi_dtxt=txt.grad.clone())
+    R = inp["txt"].shape[0] // inp["vid"].shape[0]
+    t1 = inp["txt"][::R].clone().requires_grad_(True)
+    x1 = sim_matrix(t1, inp["vid"])
+    loss, mb = egonce(x1, sim_v, sim_n, None)
+    loss.backward()
+    res.update(nce_single=loss.detach(), nce_single_mask=mb, nce_single_dtxt=t1.grad.clone())
+    loss, mb = egonce(x1.detach(), None, sim_n, None)
+    res.update(nce_noun=loss.detach(), nce_noun_mask=mb)
+    nouns = inp["nouns"].clone().requires_grad_(True)
+    pred = inp["pred"].clone().requires_grad_(True)
+    loss, cols = word_loss(nouns, pred, inp["inds"])
+    loss.backward()
+    res.update(word=loss.detach(), word_cols=cols, word_dnouns=nouns.grad.clone(), word_dpred=pred.grad.clone())
+    outputs = {"pred_logits": inp["pred_logits"], "pred_boxes": inp["pred_boxes"]}
+    targets = [{"boxes": b, "labels": l} for b, l in zip(inp["tgt_boxes"], inp["tgt_labels"])]
+    for name, excl in (("match_excl", True), ("match_cls", False)):
+        idx = matcher(outputs, targets, excl)
+        res[name + "_i"] = torch.cat([i for i, _ in idx])
+        res[name + "_j"] = torch.cat([j for _, j in idx])
+        res[name + "_n"] = torch.tensor([len(i) for i, _ in idx])
+    return res
 
 
 def subsample(case, res):
@@ -109,6 +183,18 @@ def subsample(case, res):
 def run_oracle(case):
     """The restatement's answer for a case, in the same (subsampled) form as the fixture."""
     kind = case["kind"]
+    if kind == "losses":
+        def word(nouns, pred, inds):
+            loss, cols = O.word_contrastive_loss(nouns, pred, inds)
+            return loss, torch.cat(cols)
+
+        def matcher(outputs, targets, excl):
+            tb, tl = [t["boxes"] for t in targets], [t["labels"] for t in targets]
+            if excl:
+                return O.hungarian_match(outputs["pred_boxes"], tb)
+            return O.hungarian_match(outputs["pred_boxes"], tb, outputs["pred_logits"], tl)
+        return run_losses(make_inputs(case), O.sim_matrix,
+                          lambda x, mv, mn, pad: O.egonce_loss(x, mv, mn, pad), word, matcher)
     with torch.no_grad():
         if kind == "encoder":
             c = case["cfg"]

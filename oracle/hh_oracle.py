@@ -14,7 +14,7 @@ Everything here is a function of (state_dict, inputs); state_dict keys are exact
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import List, Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -457,3 +457,72 @@ def matcher_cost(pred_cxcywh: Tensor, tgt_cxcywh: Tensor, w_bbox: float = 5.0, w
 def egonce_logprobs(sim: Tensor, temperature: float = 0.07) -> Tuple[Tensor, Tensor]:
     """The softmax part of EgoNCE.forward (model/loss.py:61-69): log-softmax over rows and columns."""
     return F.log_softmax(sim / temperature, dim=1), F.log_softmax(sim.t() / temperature, dim=1)
+
+
+# --------------------------------------------------------------------------------------------
+# training-side matching / losses  (model/box_utils.py:43-92, model/loss.py:15-106)
+# --------------------------------------------------------------------------------------------
+
+def hungarian_match(pred_boxes: Tensor, tgt_boxes: List[Tensor], pred_logits: Optional[Tensor] = None,
+                    tgt_labels: Optional[List[Tensor]] = None, cost_class: float = 1.0, cost_bbox: float = 5.0,
+                    cost_giou: float = 2.0):
+    """HungarianMatcher.forward (model/box_utils.py:43-92; weights of build_matcher :96).  `pred_logits`/`tgt_labels`
+    given <=> exclude_class=False.  scipy.optimize.linear_sum_assignment is the reference's own solver (:6,91)."""
+    from scipy.optimize import linear_sum_assignment
+    bs, Q = pred_boxes.shape[:2]
+    cost = matcher_cost(pred_boxes.flatten(0, 1), torch.cat(tgt_boxes), cost_bbox, cost_giou)
+    if pred_logits is not None:
+        prob = pred_logits.flatten(0, 1).softmax(-1)
+        cost = cost + cost_class * -prob[:, torch.cat(tgt_labels)]
+    cost = cost.view(bs, Q, -1)
+    out, start = [], 0
+    for i, t in enumerate(tgt_boxes):
+        r, c = linear_sum_assignment(cost[i, :, start:start + len(t)])
+        start += len(t)
+        out.append((torch.as_tensor(r, dtype=torch.int64), torch.as_tensor(c, dtype=torch.int64)))
+    return out
+
+
+def egonce_loss(x: Tensor, mask_v: Optional[Tensor], mask_n: Optional[Tensor], multi_pad_mask: Optional[Tensor] = None,
+                vn_threshold: float = 0.0, temperature: float = 0.07) -> Tuple[Tensor, Tensor]:
+    """EgoNCE.forward (model/loss.py:15-70).  Caption row r belongs to video r // R (R = rows / columns); rows whose pad
+    mask has a zero are filled with -inf and then dropped (:26,43-58); positives = (verb*noun | noun | verb) + diagonal,
+    times the pad mask, thresholded (:59); loss = -mean_rows(mean_pos log_softmax_row) - mean_cols(...)  (:62-70)."""
+    N, M = x.shape
+    R = 1 if multi_pad_mask is None else N // M
+    up = (lambda m: m) if R == 1 else (lambda m: m.repeat_interleave(R, 0))
+    if mask_v is not None and mask_n is not None:
+        extra = up(mask_v) * up(mask_n)
+    else:
+        extra = up(mask_n if mask_n is not None else mask_v)
+    mask = extra + up(torch.eye(M, dtype=x.dtype))
+    if multi_pad_mask is not None:
+        mask = mask * multi_pad_mask
+        keep = x.masked_fill(~multi_pad_mask.bool(), float("-inf")).sum(-1) != float("-inf")
+        mask, x = mask[keep], x[keep]
+    mb = mask > vn_threshold
+    li = (F.log_softmax(x / temperature, dim=1) * mb).sum(1) / mb.sum(1)
+    lj = (F.log_softmax(x.t() / temperature, dim=1) * mb.t()).sum(1) / mb.sum(0)
+    return -li.mean() - lj.mean(), mb
+
+
+def word_contrastive_loss(noun_embeds: Tensor, pred: Tensor, gt_inds: Tensor, temperature: float = 0.07,
+                          noun_threshold: float = 0.6):
+    """WordContrastiveLoss.forward (model/loss.py:78-106) -> (loss, [col_ind per clip with >= 1 noun])."""
+    from scipy.optimize import linear_sum_assignment
+    picked, cols = [], []
+    for b in range(gt_inds.shape[0]):
+        ids = gt_inds[b][gt_inds[b] != 0]
+        if len(ids) == 0:
+            continue
+        cost = -sim_matrix(noun_embeds[ids], pred[b]).detach()          # :85-90
+        _, col = linear_sum_assignment(cost)
+        cols.append(torch.as_tensor(col, dtype=torch.int64))
+        picked.append(pred[b][col])
+    sel = torch.cat(picked)
+    tgt = gt_inds[gt_inds != 0]
+    logits = sim_matrix(sel, noun_embeds)                                # :96
+    ns = sim_matrix(noun_embeds, noun_embeds).clone()
+    ns.fill_diagonal_(0)                                                 # :99-100
+    logits = logits.masked_fill(ns[tgt] > noun_threshold, -1) / temperature
+    return F.cross_entropy(logits, tgt), cols

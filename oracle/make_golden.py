@@ -24,6 +24,26 @@ def run_reference(case):
     ns = ref_import.import_reference()
     kind = case["kind"]
     torch.manual_seed(0)
+    if kind == "losses":
+        import importlib
+        loss_mod = importlib.import_module("model.loss")
+        box_utils = importlib.import_module("model.box_utils")
+        nce, wl = loss_mod.EgoNCE(), loss_mod.WordContrastiveLoss()
+        m = box_utils.build_matcher(None)
+
+        def word(nouns, pred, inds):
+            # the reference does not return col_ind; recompute it exactly as model/loss.py:85-93 does
+            from scipy.optimize import linear_sum_assignment
+            cols = []
+            for b in range(inds.shape[0]):
+                ids = inds[b][inds[b] != 0]
+                if len(ids):
+                    cost = -ns.metric.sim_matrix(nouns[ids], pred[b]).detach()
+                    cols.append(torch.as_tensor(linear_sum_assignment(cost)[1], dtype=torch.int64))
+            return wl(nouns, pred, inds), torch.cat(cols)
+        return gc.run_losses(gc.make_inputs(case), ns.metric.sim_matrix,
+                             lambda x, mv, mn, pad: nce(x, mv, mn, multi_pad_mask=pad, strict_mask=True), word,
+                             lambda o, t, e: m(o, t, exclude_class=e))
     with torch.no_grad():
         if kind == "encoder":
             c = case["cfg"]
