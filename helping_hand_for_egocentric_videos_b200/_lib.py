@@ -39,6 +39,7 @@ SIGNATURES = {
     "hh_encoder_set_weight": (_i, [_p, C.c_char_p, _p, _i64, _p]),
     "hh_encoder_forward": (_i, [_p, _p, _i, _p, _p]),
     "hh_encoder_forward_n": (_i, [_p, _p, _i, _i, _p, _p]),
+    "hh_encoder_forward_u8": (_i, [_p, _p, _i, C.POINTER(_f), C.POINTER(_f), _p, _p]),
     "hh_encoder_flops_per_clip": (C.c_double, [_p]),
     "hh_encoder_last_launches": (_i, [_p]),
     "hh_decoder_create": (_i, [C.POINTER(_p), C.POINTER(DecoderCfg)]),

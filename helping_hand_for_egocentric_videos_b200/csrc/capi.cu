@@ -64,6 +64,13 @@ int hh_encoder_forward_n(hh_encoder* enc, const float* video, int B, int nblocks
 int hh_encoder_forward(hh_encoder* enc, const float* video, int B, float* fmap, void* stream) {
   return hh_encoder_forward_n(enc, video, B, -1, fmap, stream);
 }
+int hh_encoder_forward_u8(hh_encoder* enc, const uint8_t* frames, int B, const float* mean, const float* stdv, float* fmap,
+                          void* stream) {
+  HH_GUARD_BEGIN
+  if (!enc) return fail(-1, "hh_encoder_forward_u8: null handle");
+  return enc->impl.forward_u8(frames, mean, stdv, B, fmap, S(stream));
+  HH_GUARD_END
+}
 double hh_encoder_flops_per_clip(const hh_encoder* enc) { return enc ? enc->impl.flops_per_clip() : 0.0; }
 int hh_encoder_last_launches(const hh_encoder* enc) { return enc ? enc->impl.launches : 0; }
 

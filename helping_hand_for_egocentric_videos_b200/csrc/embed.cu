@@ -37,6 +37,52 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ v
   }
 }
 
+// Same patch matrix from raw decoder output: frames uint8 [BT, H, W, 3] (decord / cv2 layout, base/base_dataset.py:
+// 322-323).  The loader tail  frames.float() / 255 -> permute -> NormalizeVideo(mean, std)  (data_loader/transforms.py:
+// 48-51, constants run/test_EgoMCQ.py:230-233) is applied on the fly with the reference's fp32 operation order, so the
+// bf16 patch values are bit-identical to normalising on the host first.  One thread = two horizontally adjacent pixels
+// (6 contiguous bytes in, one bf16 pair per channel out); the K..Kp padding columns are zeroed by the tail loop.
+struct NormConst { float mean[3], stdv[3]; };
+
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ frames, bf16* __restrict__ out, int BT,
+                                                        int H, int W, int p, int Kp, NormConst nc) {
+  const int gw = W / p, gh = H / p;
+  const int n = gw * gh;
+  const int hp = p >> 1;
+  const long long total = static_cast<long long>(BT) * n * p * hp;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long tid0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  for (long long i = tid0; i < total; i += stride) {
+    const int jj = static_cast<int>(i % hp) * 2;
+    long long r = i / hp;
+    const int ii = static_cast<int>(r % p);
+    r /= p;  // row = img * n + patch
+    const int patch = static_cast<int>(r % n);
+    const int img = static_cast<int>(r / n);
+    const int py = patch / gw, px = patch - py * gw;
+    const uint8_t* s = frames + ((static_cast<size_t>(img) * H + (py * p + ii)) * W + px * p + jj) * 3;
+    const ushort3 raw = *reinterpret_cast<const ushort3*>(s);  // 6 bytes, 2-byte aligned (even pixel column)
+    const float u[6] = {static_cast<float>(raw.x & 0xff), static_cast<float>(raw.x >> 8), static_cast<float>(raw.y & 0xff),
+                        static_cast<float>(raw.y >> 8), static_cast<float>(raw.z & 0xff), static_cast<float>(raw.z >> 8)};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v0 = __fdiv_rn(__fsub_rn(__fdiv_rn(u[c], 255.f), nc.mean[c]), nc.stdv[c]);
+      const float v1 = __fdiv_rn(__fsub_rn(__fdiv_rn(u[3 + c], 255.f), nc.mean[c]), nc.stdv[c]);
+      *reinterpret_cast<uint32_t*>(out + r * Kp + c * p * p + ii * p + jj) = pack_bf16x2(v0, v1);
+    }
+  }
+  const int K = 3 * p * p;
+  const int padh = (Kp - K) >> 1;
+  if (padh > 0) {
+    const long long ptotal = static_cast<long long>(BT) * n * padh;
+    for (long long i = tid0; i < ptotal; i += stride) {
+      const long long row = i / padh;
+      const int k = K + static_cast<int>(i % padh) * 2;
+      *reinterpret_cast<uint32_t*>(out + row * Kp + k) = 0u;
+    }
+  }
+}
+
 constexpr int MAX_VEC = 8;
 
 __global__ void __launch_bounds__(256)
@@ -115,6 +161,26 @@ int im2col_patches(const float* video, bf16* out, int BT, int H, int W, int p, i
   if (blocks > cap) blocks = cap;
   im2col_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(video, out, BT, H, W, p, Kp);
   HH_CHECK_LAUNCH("im2col_kernel");
+  return 0;
+}
+
+int im2col_patches_u8(const uint8_t* frames, const float* mean, const float* stdv, bf16* out, int BT, int H, int W, int p,
+                      int Kp, cudaStream_t stream) {
+  HH_REQUIRE(p % 2 == 0 && H % p == 0 && W % p == 0, "im2col_patches_u8: patch size must be even and divide H, W");
+  HH_REQUIRE(Kp % 8 == 0 && Kp >= 3 * p * p, "im2col_patches_u8: padded K");
+  HH_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 1) == 0, "im2col_patches_u8: frames must be 2-byte aligned");
+  HH_REQUIRE(stdv[0] != 0.f && stdv[1] != 0.f && stdv[2] != 0.f, "im2col_patches_u8: zero std");
+  NormConst nc;
+  for (int c = 0; c < 3; ++c) {
+    nc.mean[c] = mean[c];
+    nc.stdv[c] = stdv[c];
+  }
+  const long long total = static_cast<long long>(BT) * (H / p) * (W / p) * p * (p / 2);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  im2col_u8_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(frames, out, BT, H, W, p, Kp, nc);
+  HH_CHECK_LAUNCH("im2col_u8_kernel");
   return 0;
 }
 

@@ -205,8 +205,19 @@ int Encoder::pack(cudaStream_t s) {
 }
 
 int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaStream_t s) {
+  HH_REQUIRE(video != nullptr, "encoder forward: null buffer");
+  return run(video, nullptr, nullptr, nullptr, B, nblocks, fmap, s);
+}
+
+int Encoder::forward_u8(const uint8_t* frames, const float* mean, const float* stdv, int B, float* fmap, cudaStream_t s) {
+  HH_REQUIRE(frames != nullptr && mean != nullptr && stdv != nullptr, "encoder forward_u8: null buffer");
+  return run(nullptr, frames, mean, stdv, B, -1, fmap, s);
+}
+
+int Encoder::run(const float* video, const uint8_t* frames, const float* mean, const float* stdv, int B, int nblocks,
+                 float* fmap, cudaStream_t s) {
   HH_REQUIRE(B > 0, "encoder forward: empty batch");
-  HH_REQUIRE(video != nullptr && fmap != nullptr, "encoder forward: null buffer");
+  HH_REQUIRE(fmap != nullptr, "encoder forward: null buffer");
   if (weights.dirty) RC(pack(s));
   if (nblocks < 0 || nblocks > cfg.depth) nblocks = cfg.depth;
   launches = 0;
@@ -237,9 +248,14 @@ int Encoder::forward(const float* video, int B, int nblocks, float* fmap, cudaSt
     const int Bc = (B - b0) < chunk ? (B - b0) : chunk;
     const int M = Bc * N;
     const int P = Bc * T * n;
-    const float* vid = video + static_cast<size_t>(b0) * T * frame_elems;
     // patch embed (LaviLa.py:218-223,540-542) + CLS/pos/temporal + ln_pre (:545-559)
-    PROF(K_EMBED, im2col_patches(vid, patches, Bc * T, cfg.img_size, cfg.img_size, cfg.patch_size, Kp, s));
+    if (frames) {
+      PROF(K_EMBED, im2col_patches_u8(frames + static_cast<size_t>(b0) * T * frame_elems, mean, stdv, patches, Bc * T,
+                                      cfg.img_size, cfg.img_size, cfg.patch_size, Kp, s));
+    } else {
+      PROF(K_EMBED, im2col_patches(video + static_cast<size_t>(b0) * T * frame_elems, patches, Bc * T, cfg.img_size,
+                                   cfg.img_size, cfg.patch_size, Kp, s));
+    }
     PROF(K_GEMM_PATCH, gemm_bf16(patches, Kp, static_cast<const bf16*>(w_patch.ptr), Kp, tok, D, nullptr, nullptr, 0, P, D,
                                  Kp, EPI_BIAS_F32, s));
     PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),

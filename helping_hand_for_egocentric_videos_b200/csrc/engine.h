@@ -69,7 +69,15 @@ struct Encoder {
   static int validate(const hh_encoder_cfg& c);
   int pack(cudaStream_t s);
   int forward(const float* video, int B, int nblocks, float* fmap, cudaStream_t s);
+  // raw frames uint8 [B,T,H,W,3] with the loader's /255 + mean/std normalisation fused into the patch loader
+  int forward_u8(const uint8_t* frames, const float* mean, const float* stdv, int B, float* fmap, cudaStream_t s);
   double flops_per_clip() const;
+
+ private:
+  int run(const float* video, const uint8_t* frames, const float* mean, const float* stdv, int B, int nblocks, float* fmap,
+          cudaStream_t s);
+
+ public:
 };
 
 struct Decoder {

@@ -69,6 +69,9 @@ int cast_rows_bf16(const float* src, long long outer_stride, long long row_strid
 // ---------------------------------------------------------------- encoder satellites (embed.cu)
 // video fp32 [B*T,3,H,W] -> patches bf16 [B*T*n, Kp] (k = c*p*p + i*p + j, zero padded to Kp).
 int im2col_patches(const float* video, bf16* out, int BT, int H, int W, int p, int Kp, cudaStream_t stream);
+// frames uint8 [B*T,H,W,3] -> the same patch matrix with ((u/255) - mean[c]) / std[c] applied on the fly (host arrays).
+int im2col_patches_u8(const uint8_t* frames, const float* mean, const float* stdv, bf16* out, int BT, int H, int W, int p,
+                      int Kp, cudaStream_t stream);
 // x[b, 0] = LN(cls + pos[0]); x[b, 1 + f*n + q] = LN(tok[(b*T+f)*n + q] + pos[1+q] + temporal[f]);  eps 1e-5
 int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, const float* temporal, const float* w,
                        const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream);

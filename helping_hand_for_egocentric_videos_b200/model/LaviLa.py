@@ -234,6 +234,31 @@ class SpaceTimeTransformer(nn.Module):
         x_cls = self.pre_logits(fmap[:, 0])
         return x_cls, fmap
 
+    @torch.no_grad()
+    def forward_features_u8(self, frames, norm_mean, norm_std):
+        """Raw decoder output uint8 [B,T,H,W,3] -> (x_cls, fmap), with the loader tail of the reference
+        (frames.float()/255, permute, NormalizeVideo(mean, std): base/base_dataset.py:322-323,
+        data_loader/transforms.py:48-51) fused into the patch loader.  Bit-identical to
+        forward_features(((frames.float() / 255).permute(0, 1, 4, 2, 3) - mean) / std)."""
+        if not frames.is_cuda:
+            raise RuntimeError("SpaceTimeTransformer (B200): input is on %s; there is no CPU fallback" % frames.device)
+        if frames.dtype != torch.uint8:
+            raise TypeError("forward_features_u8 expects uint8 frames, got %s" % frames.dtype)
+        b, t, hh, ww, c = frames.shape
+        if t != self.temporal_embed.shape[1]:
+            raise RuntimeError("got %d frames, model built for %d" % (t, self.temporal_embed.shape[1]))
+        if c != 3 or hh != self._cfg.img_size or ww != self._cfg.img_size:
+            raise RuntimeError("expected [B,T,%d,%d,3] frames, got %s" % (self._cfg.img_size, self._cfg.img_size,
+                                                                         tuple(frames.shape)))
+        self.sync_weights()
+        frames = frames.contiguous()
+        mean = (C.c_float * 3)(*[float(v) for v in norm_mean])
+        std = (C.c_float * 3)(*[float(v) for v in norm_std])
+        fmap = torch.empty(b, 1 + t * self.patches_per_frame, self.embed_dim, dtype=torch.float32, device=frames.device)
+        L.check(L.load().hh_encoder_forward_u8(self._engine(), L.ptr(frames), b, mean, std, L.ptr(fmap), L.stream_ptr()),
+                "hh_encoder_forward_u8")
+        return self.pre_logits(fmap[:, 0]), fmap
+
     def forward(self, x, use_checkpoint=False):
         x_cls, x = self.forward_features(x, use_checkpoint=use_checkpoint)
         return self.head(x_cls), x

@@ -54,6 +54,13 @@ int hh_encoder_forward(hh_encoder* enc, const float* video, int B, float* fmap, 
 /* Test hook: fp32 residual stream after block `block` (0-based) of the last forward is not retained; instead run a
  * truncated forward: blocks [0, nblocks) then the final norm. nblocks < 0 means all. */
 int hh_encoder_forward_n(hh_encoder* enc, const float* video, int B, int nblocks, float* fmap, void* stream);
+/* Same forward from raw decoder output: frames uint8 [B,T,H,W,3] (decord / cv2 layout, base/base_dataset.py:322-323).
+ * The loader tail `frames.float()/255 -> permute -> NormalizeVideo(mean, std)` (data_loader/transforms.py:48-51; constants
+ * run/test_EgoMCQ.py:230-233) is applied inside the patch loader in the reference's fp32 operation order, so the result
+ * is bit-identical to hh_encoder_forward on the host-normalised clip, at a quarter of the input bytes.
+ * mean / std: 3 host floats each (per channel, in [0,1] units). */
+int hh_encoder_forward_u8(hh_encoder* enc, const uint8_t* frames, int B, const float* mean, const float* std,
+                          float* fmap, void* stream);
 /* Algorithmic FLOPs of one clip through the encoder (SURVEY.md section 8d formula). */
 double hh_encoder_flops_per_clip(const hh_encoder* enc);
 /* Number of kernel launches issued by the last hh_encoder_forward call. */

@@ -110,6 +110,27 @@ def test_text_tower_full_depth_against_oracle(width, heads, G):
         clip.encode_text(tokens)
 
 
+@pytest.mark.parametrize("name", ["enc_tiny", "enc_c0"])
+def test_uint8_frames_equal_host_normalised_clip(name):
+    """SURVEY section 8f row 3: the loader tail (base/base_dataset.py:322-323 `frames.float()/255`, `permute`;
+    data_loader/transforms.py:48-51 NormalizeVideo with the constants of run/test_EgoMCQ.py:230-233) fused into the patch
+    loader gives bit-identical features to normalising on the host and calling the fp32 entry point."""
+    case = gc.CASES[name]
+    clip, _ = _build_backbone(case)
+    c = case["cfg"]
+    g = torch.Generator().manual_seed(77)
+    frames = torch.randint(0, 256, (2, c["T"], c["img"], c["img"], 3), generator=g, dtype=torch.uint8)
+    mean = [108.3272985 / 255, 116.7460125 / 255, 104.09373615000001 / 255]
+    std = [68.5005327 / 255, 66.6321579 / 255, 70.32316305 / 255]
+    x = (frames.to(torch.float32) / 255).permute(0, 1, 4, 2, 3).contiguous()          # [B,T,3,H,W] on the host
+    x = x.sub_(torch.tensor(mean)[None, None, :, None, None]).div_(torch.tensor(std)[None, None, :, None, None])
+    cls_a, fmap_a = clip.visual.forward_features(x.cuda())
+    cls_b, fmap_b = clip.visual.forward_features_u8(frames.cuda(), mean, std)
+    assert torch.equal(fmap_a, fmap_b) and torch.equal(cls_a, cls_b)
+    with pytest.raises(TypeError):
+        clip.visual.forward_features_u8(frames.cuda().float(), mean, std)
+
+
 def test_encoder_blocks_against_oracle():
     """Per-depth parity: truncated forwards (1, 2 blocks) against the oracle's per-block activations."""
     case = gc.CASES["enc_tiny"]
