@@ -63,6 +63,7 @@ SIGNATURES = {
     "hh_word_loss_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "hh_word_loss_forward": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "hh_word_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hh_retrieval_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "hh_attention_causal": (_i, [_p, _p, _i, _i, _i, _p]),
     "hh_profile_num_classes": (_i, []),
     "hh_profile_class_name": (C.c_char_p, [_i]),

@@ -236,6 +236,11 @@ int hh_word_loss_backward(const float* noun_embeds, int V, int d, int B2, int Q,
                             stats, grad_loss, d_pred, d_nouns, workspace, S(stream));
 }
 
+int hh_retrieval_rows(const double* sim, const double* rel, const double* logs, const int32_t* kcounts, int N, int M,
+                      int mode, double* out, void* stream) {
+  return retrieval_rows(sim, rel, logs, kcounts, N, M, mode, out, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------ kernel-level entry points
 int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
                  const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream) {

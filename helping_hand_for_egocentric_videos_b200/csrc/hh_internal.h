@@ -182,4 +182,10 @@ int word_loss_backward(const float* nouns, int V, int d, int B2, int Q, int Wm, 
                        const float* dlogits, const float* stats, const float* grad_loss, float* d_pred, float* d_nouns,
                        void* workspace, cudaStream_t s);
 
+// ---------------------------------------------------------------- retrieval metrics (retrieval.cu)
+// Per query row of sim [N, M] (float64): mode 0 -> average precision (utils/mAP.py), mode 1 -> DCG (utils/nDCG.py) with
+// logs[k] = log2(k + 2) and the optional k_counts mask (null: first #(rel > 0) ranks).  out float64 [N].
+int retrieval_rows(const double* sim, const double* rel, const double* logs, const int* kcounts, int N, int M, int mode,
+                   double* out, cudaStream_t stream);
+
 }  // namespace hh

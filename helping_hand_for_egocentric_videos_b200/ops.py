@@ -225,3 +225,27 @@ def sim_matrix_backward(a: torch.Tensor, b: torch.Tensor, grad: torch.Tensor, ep
     L.check(lib.hh_sim_matrix_backward(L.ptr(a), L.ptr(b), L.ptr(grad), None, L.ptr(da), L.ptr(db), Na, Nb, d, eps,
                                        L.ptr(ws), L.stream_ptr()), "hh_sim_matrix_backward")
     return da, db
+
+
+def retrieval_rows(sim, rel, mode: int, kcounts=None):
+    """Per-query average precision (mode 0, utils/mAP.py) or DCG (mode 1, utils/nDCG.py) on the device, float64.
+    `sim`, `rel` [N, M]: numpy arrays or tensors (moved to the current CUDA device).  Returns a float64 numpy vector [N]."""
+    import numpy as np
+
+    def dev64(x):
+        t = torch.as_tensor(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+        return t.to(device="cuda", dtype=torch.float64).contiguous()
+    s, r = dev64(sim), dev64(rel)
+    assert s.dim() == 2 and s.shape == r.shape, "similarity and relevancy matrices must have the same 2-D shape"
+    N, M = s.shape
+    out = torch.empty(N, dtype=torch.float64, device=s.device)
+    logs = kc = None
+    if mode == 1:
+        logs = torch.from_numpy(np.log2(np.arange(M) + 2)).to(s.device)          # numpy's own divisor table
+        if kcounts is not None:
+            kc = torch.as_tensor(np.ascontiguousarray(kcounts) if isinstance(kcounts, np.ndarray) else kcounts)
+            kc = kc.to(device=s.device, dtype=torch.int32).contiguous()
+            assert kc.shape == s.shape
+    L.check(L.load().hh_retrieval_rows(L.ptr(s), L.ptr(r), L.ptr(logs), L.ptr(kc), N, M, mode, L.ptr(out),
+                                       L.stream_ptr()), "hh_retrieval_rows")
+    return out.cpu().numpy()

@@ -235,6 +235,15 @@ int hh_word_loss_backward(const float* noun_embeds, int V, int d, int B2, int Q,
                           float* d_pred, float* d_nouns, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Retrieval metrics (run/test_epic.py:262-283): per-query average precision (utils/mAP.py:4-44, mode 0) or discounted
+ * cumulative gain (utils/nDCG.py:3-44, mode 1) of sim [N, M] against rel [N, M], all float64 device arrays, M <= 16384.
+ * logs [M] = log2(k + 2) (mode 1; pass numpy's table so the divisors are the reference's own); kcounts int32 [N, M] or
+ * NULL (= calculate_k_counts(rel), utils/nDCG.py:46-75).  out float64 [N].  Summation follows numpy's order (sequential
+ * cumsum, pairwise np.sum), so results equal the reference's bit for bit when no two similarities of a row tie. */
+int hh_retrieval_rows(const double* sim, const double* rel, const double* logs, const int32_t* kcounts, int N, int M,
+                      int mode, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Data-parallel exchange: the one collective of the path (all-gather of embeddings for the cross-rank similarity
  * matrix, run/train.py:36-37,126-128; _valid_all_gather, utils/train_utils.py:51-59).  NCCL is resolved at run time
  * (dlopen of the libnccl.so.2 already loaded by the host framework); one communicator per process / GPU.

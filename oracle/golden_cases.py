@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE ONLY.  Inputs and weights are regenerated from seeds; fixtur
 """
 import os
 
+import numpy as np
 import torch
 
 from . import hh_oracle as O
@@ -226,3 +227,21 @@ def run_oracle(case):
             return {"sim": O.sim_matrix(a, b), "sim3": O.sim_matrix(a[None], b[None]),
                     "acc": O.egomcq_accuracy(preds, labels, types)}
     raise ValueError(kind)
+
+
+# ---- retrieval metrics: the reference's known-answer vector (utils/nDCG.py:154-172) and EPIC-MIR-like synthetic input
+KNOWN_SIM = np.array([[1.0, 0.7, 0.4, 0.0], [0.3, 0.9, 0.6, 0.1], [0.2, 0.5, 0.8, 0.4]])
+KNOWN_REL = np.array([[1.0, 0.5, 0.25, 0.0], [0.0, 1.0, 0.4, 0.0], [0.5, 0.3, 1.0, 0.0]])
+KNOWN_K = np.array([[1, 1, 1, 0], [1, 1, 0, 0], [1, 1, 1, 0]])
+KNOWN_NDCG = 0.9371789900735429            # utils/nDCG.py:172
+
+
+def synth_retrieval(N, M, seed):
+    """EPIC-MIR-like inputs: float64 similarities without ties, relevancies in {0, fractions, 1} with >= 1 exact one per row and column."""
+    rng = np.random.RandomState(seed)
+    sim = rng.randn(N, M)
+    rel = np.where(rng.rand(N, M) < 0.02, np.round(rng.rand(N, M), 2), 0.0)
+    rel[rng.rand(N, M) < 0.004] = 1.0
+    rel[np.arange(N), rng.randint(0, M, N)] = 1.0
+    rel[rng.randint(0, N, M), np.arange(M)] = 1.0          # ... in both retrieval directions
+    return sim, rel

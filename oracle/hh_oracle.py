@@ -526,3 +526,45 @@ def word_contrastive_loss(noun_embeds: Tensor, pred: Tensor, gt_inds: Tensor, te
     ns.fill_diagonal_(0)                                                 # :99-100
     logits = logits.masked_fill(ns[tgt] > noun_threshold, -1) / temperature
     return F.cross_entropy(logits, tgt), cols
+
+
+# --------------------------------------------------------------------------------------------
+# retrieval metrics  (utils/mAP.py, utils/nDCG.py; numpy float64 like the reference)
+# --------------------------------------------------------------------------------------------
+
+def calculate_mAP(sim_mat, relevancy_matrix):
+    """utils/mAP.py:4-44: AP_q = sum_k [rel_k == 1] * cumsum(rel)_k / (k+1) / #(rel == 1) over the ranking by descending
+    similarity (note: the cumulative sum runs over ALL relevancy values, fractional ones included); mean over queries."""
+    import numpy as np
+    order = np.argsort(-sim_mat, axis=1, kind="stable")
+    rows = np.arange(sim_mat.shape[0])[:, None]
+    ranked = relevancy_matrix[rows, order]
+    hits = ranked == 1
+    cum = np.where(hits, np.cumsum(ranked, axis=1), 0)
+    ap = np.sum(cum / (np.arange(ranked.shape[1]) + 1), axis=1) / hits.sum(axis=1)
+    return np.mean(ap), ap
+
+
+def calculate_DCG(similarity_matrix, relevancy_matrix, k_counts):
+    """utils/nDCG.py:3-44: sum_k rel[rank_k] * k_counts[k] / log2(k + 2), ranking = argsort(sim)[::-1]."""
+    import numpy as np
+    order = np.argsort(similarity_matrix, axis=1, kind="stable")[:, ::-1]
+    rows = np.arange(similarity_matrix.shape[0])[:, None]
+    return np.sum(relevancy_matrix[rows, order] * k_counts / np.log2(np.arange(similarity_matrix.shape[1]) + 2), axis=1)
+
+
+def calculate_k_counts(relevancy_matrix):
+    """utils/nDCG.py:46-75."""
+    import numpy as np
+    return (np.sort(relevancy_matrix)[:, ::-1] > 0).astype(int)
+
+
+def calculate_nDCG(similarity_matrix, relevancy_matrix, k_counts=None, IDCG=None):
+    """utils/nDCG.py:97-150 with reduction='mean'; also returns the per-query vector."""
+    import numpy as np
+    if k_counts is None:
+        k_counts = calculate_k_counts(relevancy_matrix)
+    dcg = calculate_DCG(similarity_matrix, relevancy_matrix, k_counts)
+    if IDCG is None:
+        IDCG = calculate_DCG(relevancy_matrix, relevancy_matrix, k_counts)
+    return np.mean(dcg / IDCG), dcg / IDCG

@@ -195,3 +195,25 @@ def test_sim_matrix_backward_with_clamped_rows():
     _close(da[torch.arange(37) != 3], a0.grad[torch.arange(37) != 3], "da")
     _close(db, b0.grad, "db", rtol=1e-4)
     assert torch.isfinite(da).all()
+
+
+# ------------------------------------------------------------------------------------------ retrieval metrics (f-4)
+def test_retrieval_known_answer_and_oracle():
+    """utils/nDCG.py:154-181 known answer, then mAP / nDCG against the oracle at growing sizes up to one EPIC-MIR-sized
+    row length (9668 candidates).  float64, numpy's summation order: equality is exact."""
+    from helping_hand_for_egocentric_videos_b200.utils import mAP, nDCG
+    from oracle.golden_cases import KNOWN_K, KNOWN_NDCG, KNOWN_REL, KNOWN_SIM, synth_retrieval
+    assert (nDCG.calculate_k_counts(KNOWN_REL) == KNOWN_K).all()
+    assert nDCG.calculate_nDCG(KNOWN_SIM, KNOWN_REL, KNOWN_K) == KNOWN_NDCG
+    idcg = nDCG.calculate_IDCG(KNOWN_REL, KNOWN_K)
+    assert nDCG.calculate_nDCG(KNOWN_SIM, KNOWN_REL, KNOWN_K, IDCG=idcg) == KNOWN_NDCG
+    assert np.mean(nDCG.calculate_nDCG(KNOWN_SIM, KNOWN_REL, KNOWN_K, IDCG=idcg, reduction=None)) == KNOWN_NDCG
+    for N, M, seed in [(5, 7, 0), (40, 300, 1), (33, 2000, 2), (24, 9668, 3)]:
+        sim, rel = synth_retrieval(N, M, seed)
+        want_map, want_ap = O.calculate_mAP(sim, rel)
+        want_ndcg, want_rows = O.calculate_nDCG(sim, rel)
+        assert mAP.calculate_mAP(sim, rel) == want_map, (N, M)
+        assert np.array_equal(nDCG.calculate_nDCG(sim, rel, reduction=None), want_rows), (N, M)
+        assert nDCG.calculate_nDCG(sim, rel) == want_ndcg
+        # the text->video direction of run/test_epic.py:271-278 (transposed, non-contiguous inputs)
+        assert mAP.calculate_mAP(sim.T, rel.T) == O.calculate_mAP(sim.T.copy(), rel.T.copy())[0]
