@@ -54,6 +54,8 @@ SIGNATURES = {
     "hh_text_forward": (_i, [_p, _p, _i, _p, _p, _p]),
     "hh_text_flops_per_sequence": (C.c_double, [_p]),
     "hh_text_last_launches": (_i, [_p]),
+    "hh_box_loss_forward": (_i, [_p, _p, _p, _i, _f, _p, _p]),
+    "hh_box_loss_backward": (_i, [_p, _p, _p, _i, _f, _p, _p, _i64, _p]),
     "hh_assign": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p]),
     "hh_match_cost_class": (_i, [_p, _i, _i, _p, _i, _f, _p, _p]),
     "hh_sim_matrix_backward_workspace_bytes": (_sz, [_i, _i]),

@@ -192,6 +192,15 @@ int hh_box_match_cost(const float* pred, const float* tgt, int N, int M, float w
   return box_match_cost(pred, tgt, N, M, w_bbox, w_giou, cost, S(stream));
 }
 
+int hh_box_loss_forward(const float* pred, const int64_t* src_row, const float* tgt, int K, float num_boxes,
+                        float* losses, void* stream) {
+  return box_loss_forward(pred, reinterpret_cast<const long long*>(src_row), tgt, K, num_boxes, losses, S(stream));
+}
+int hh_box_loss_backward(const float* pred, const int64_t* src_row, const float* tgt, int K, float num_boxes,
+                         const float* g_losses, float* grad_pred, int64_t pred_rows, void* stream) {
+  return box_loss_backward(pred, reinterpret_cast<const long long*>(src_row), tgt, K, num_boxes, g_losses, grad_pred,
+                           pred_rows, S(stream));
+}
 int hh_assign(const float* cost, const int64_t* offset, const int32_t* ld, const int32_t* nr, const int32_t* nc,
               const uint8_t* row_valid, int row_valid_ld, int P, int max_dim, int64_t* row_ind, int64_t* col_ind,
               int32_t* count, int out_ld, void* stream) {

@@ -149,6 +149,12 @@ int box_pairwise(const float* b1, const float* b2, int N, int M, float* iou, flo
 int box_match_cost(const float* pred, const float* tgt, int N, int M, float w_bbox, float w_giou, float* cost,
                    cudaStream_t stream);
 
+// matched-pair box loss (SetCriterion.loss_boxes, model/box_utils.py:157-173): losses[0] = L1 / num_boxes,
+// losses[1] = sum(1 - giou) / num_boxes over pairs (pred[src_row[k]], tgt[k]), both cxcywh; and its gradient w.r.t. pred.
+int box_loss_forward(const float* pred, const long long* src_row, const float* tgt, int K, float num_boxes, float* losses,
+                     cudaStream_t stream);
+int box_loss_backward(const float* pred, const long long* src_row, const float* tgt, int K, float num_boxes,
+                      const float* g_losses, float* grad_pred, long long pred_rows, cudaStream_t stream);
 
 // ---------------------------------------------------------------- assignment (assign.cu)
 // P independent rectangular linear-sum-assignment problems (scipy.optimize.linear_sum_assignment semantics and index

@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .. import ops
+from ..utils.checkpoint import remap_keys  # noqa: F401  (reference model/LaviLa.py:19-53 lives in this module)
 
 
 class QuickGELU(nn.Module):

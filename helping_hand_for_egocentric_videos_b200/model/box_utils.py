@@ -1,4 +1,6 @@
-"""Mirror of the matcher of the reference's ``model/box_utils.py`` (HungarianMatcher :15-92, build_matcher :95-96).
+"""Mirror of the training-side box utilities of the reference's ``model/box_utils.py``: HungarianMatcher (:15-92),
+build_matcher (:95-96), SetCriterion (:99-238), prepare_targets (:249-279), split_detr_out (:433-443) and
+compute_box_loss (:446-461).
 
 Same constructor, ``forward(outputs, targets, exclude_class=False)`` signature and return value (a list with one
 ``(index_i, index_j)`` pair of int64 CPU tensors per image).  The reference copies the whole cost matrix to the host and
@@ -12,6 +14,7 @@ import torch
 from torch import nn
 
 from .. import ops
+from ..utils import box_ops
 
 
 class HungarianMatcher(nn.Module):
@@ -58,3 +61,166 @@ class HungarianMatcher(nn.Module):
 
 def build_matcher(args):
     return HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
+
+
+# ---------------------------------------------------------------------------------------------- criterion
+class _BoxLossFn(torch.autograd.Function):
+    """(loss_bbox, loss_giou) of matched prediction / target pairs with the hand-written backward kernel."""
+
+    @staticmethod
+    def forward(ctx, pred_flat, src_row, tgt, num_boxes):
+        from .. import _lib as L
+        losses = torch.empty(2, dtype=torch.float32, device=pred_flat.device)
+        K = src_row.numel()
+        L.check(L.load().hh_box_loss_forward(L.ptr(pred_flat), L.ptr(src_row), L.ptr(tgt), K, float(num_boxes),
+                                             L.ptr(losses), L.stream_ptr()), "hh_box_loss_forward")
+        ctx.save_for_backward(pred_flat, src_row, tgt)
+        ctx.num_boxes = float(num_boxes)
+        return losses[0].clone(), losses[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_bbox, g_giou):
+        from .. import _lib as L
+        pred_flat, src_row, tgt = ctx.saved_tensors
+        g = torch.stack([g_bbox, g_giou]).float().contiguous()
+        grad = torch.empty_like(pred_flat)
+        L.check(L.load().hh_box_loss_backward(L.ptr(pred_flat), L.ptr(src_row), L.ptr(tgt), src_row.numel(), ctx.num_boxes,
+                                              L.ptr(g), L.ptr(grad), pred_flat.shape[0], L.stream_ptr()),
+                "hh_box_loss_backward")
+        return grad, None, None, None
+
+
+def is_dist_avail_and_initialized():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if is_dist_avail_and_initialized() else 1
+
+
+class SetCriterion(nn.Module):
+    """Reference model/box_utils.py:99-238 (DETR criterion restricted, as there, to the 'boxes' and 'cardinality'
+    losses): Hungarian matching of the last layer's outputs, then L1 + GIoU on the matched pairs.  Matching, both loss
+    terms and their gradient are device kernels (hh_assign, hh_box_loss_*)."""
+
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses):
+        super().__init__()
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.weight_dict = weight_dict
+        self.eos_coef = eos_coef
+        self.losses = losses
+        empty_weight = torch.ones(num_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        self.register_buffer('empty_weight', empty_weight)
+
+    @torch.no_grad()
+    def loss_cardinality(self, outputs, targets, indices, num_boxes, box_type):
+        pred_logits = outputs['pred_logits']
+        tgt_lengths = torch.as_tensor([len(v["labels"]) for v in targets], device=pred_logits.device)
+        top = ops.row_argmax(pred_logits.flatten(0, 1)).view(pred_logits.shape[:2])
+        card_pred = (top != pred_logits.shape[-1] - 1).sum(1)
+        card_err = (card_pred.float() - tgt_lengths.float()).abs().mean()
+        return {f'cardinality_error_{box_type}': card_err}
+
+    def loss_boxes(self, outputs, targets, indices, num_boxes, box_type):
+        assert 'pred_boxes' in outputs
+        pred = outputs['pred_boxes']
+        batch_idx, src_idx = self._get_src_permutation_idx(indices)
+        src_row = (batch_idx * pred.shape[1] + src_idx).to(pred.device)
+        target_boxes = torch.cat([t['boxes'][i.to(t['boxes'].device)] for t, (_, i) in zip(targets, indices)], dim=0)
+        pred_flat = pred.flatten(0, 1)
+        if pred_flat.dtype != torch.float32 or not pred_flat.is_contiguous():
+            pred_flat = pred_flat.float().contiguous()
+        loss_bbox, loss_giou = _BoxLossFn.apply(pred_flat, src_row.contiguous(),
+                                                target_boxes.to(pred.device).float().contiguous(), num_boxes)
+        return {f'loss_bbox_{box_type}': loss_bbox, f'loss_giou_{box_type}': loss_giou}
+
+    def _get_src_permutation_idx(self, indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        src_idx = torch.cat([src for (src, _) in indices])
+        return batch_idx, src_idx
+
+    def _get_tgt_permutation_idx(self, indices):
+        batch_idx = torch.cat([torch.full_like(tgt, i) for i, (_, tgt) in enumerate(indices)])
+        tgt_idx = torch.cat([tgt for (_, tgt) in indices])
+        return batch_idx, tgt_idx
+
+    def get_loss(self, loss, outputs, targets, indices, num_boxes, box_type, **kwargs):
+        loss_map = {'cardinality': self.loss_cardinality, 'boxes': self.loss_boxes}
+        assert loss in loss_map, f'do you really want to compute {loss} loss?'
+        return loss_map[loss](outputs, targets, indices, num_boxes, box_type, **kwargs)
+
+    def forward(self, outputs, targets, box_type, exclude_class=False):
+        outputs_without_aux = {k: v for k, v in outputs.items() if k != 'aux_outputs'}
+        indices_last = self.matcher(outputs_without_aux, targets, exclude_class=exclude_class)
+        num_boxes = sum(len(t["labels"]) for t in targets)
+        num_boxes = torch.as_tensor([num_boxes], dtype=torch.float, device=next(iter(outputs.values())).device)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+        losses = {}
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, indices_last, num_boxes, box_type))
+        if 'aux_outputs' in outputs:
+            for i, aux_outputs in enumerate(outputs['aux_outputs']):
+                indices = self.matcher(aux_outputs, targets, exclude_class=exclude_class)
+                for loss in self.losses:
+                    l_dict = self.get_loss(loss, aux_outputs, targets, indices, num_boxes, box_type)
+                    losses.update({k + f'_{i}': v for k, v in l_dict.items()})
+        return losses, indices_last
+
+
+@torch.no_grad()
+def prepare_targets(boxes, classes, image_size, center_crop=True):
+    """Reference :249-279: xyxy pixel boxes -> per-image dicts of normalised cxcywh boxes (absent / degenerate boxes
+    dropped).  Unlike the reference (:255 `.cuda()`), tensors stay on the device of `boxes`."""
+    if classes is None:
+        classes = torch.stack([1 - (box.sum(-1) != 0).float() for box in boxes]).to(boxes.device)
+    if center_crop:
+        shift = torch.zeros_like(boxes)
+        dis = (image_size[:, 1] - image_size[:, 0]) / 2
+        wide, tall = dis >= 0, dis < 0
+        shift[wide, :, 0] = -dis[wide, None]
+        shift[wide, :, 2] = -dis[wide, None]
+        shift[tall, :, 1] = dis[tall, None]
+        shift[tall, :, 3] = dis[tall, None]
+        boxes += shift
+        boxes = torch.clip(boxes, min=0, max=256).div(256)
+    else:
+        boxes = torch.clip(boxes, min=0, max=224).div(224)
+    out = []
+    for c_, b_ in zip(classes, boxes):
+        avail = (c_ != -1) * (b_[:, 2] > b_[:, 0]) * (b_[:, 3] > b_[:, 1])
+        kept = b_[avail, :]
+        out.append({'labels': c_[avail], 'boxes': box_ops.box_xyxy_to_cxcywh(kept)})
+    return out
+
+
+def split_detr_out(detr_out, start=0, end=2):
+    """Reference :433-443, including its quirk: 'aux_outputs' is emptied before it is iterated, so the auxiliary
+    decoder layers never contribute a box loss."""
+    out = detr_out.copy()
+    out['pred_boxes'] = detr_out['pred_boxes'][:, start:end, :]
+    out['pred_logits'] = detr_out['pred_logits'][:, start:end]
+    out['aux_outputs'] = []
+    return out
+
+
+def compute_box_loss(box_type, criterion, detr_out, target_boxes, target_classes, all_image_size, n_queries=10):
+    """Reference :446-461."""
+    targets = prepare_targets(target_boxes, target_classes, all_image_size, center_crop=False)
+    if box_type == 'hand_boxes':
+        detr_pred = split_detr_out(detr_out, start=0, end=2)
+    elif box_type == 'obj_boxes':
+        detr_pred = split_detr_out(detr_out, start=2, end=n_queries)
+    elif box_type == 'all_boxes':
+        detr_pred = detr_out
+    detr_loss_dict, matched_indices = criterion(detr_pred, targets, box_type, exclude_class=True)
+    weight_dict = criterion.weight_dict
+    for k in detr_loss_dict.keys():
+        if k in weight_dict:
+            detr_loss_dict[k] *= weight_dict[k]
+    return sum(v for k, v in detr_loss_dict.items() if k in weight_dict) / (len(weight_dict) / 3), matched_indices

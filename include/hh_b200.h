@@ -184,6 +184,15 @@ int hh_attention_causal(const void* qkv, void* out, int G, int L, int H, void* s
 int hh_cross_attention_simt(const float* q, const void* K, const void* V, int ldkv, float* out, int B, int Q, int heads,
                             int S, void* stream);
 
+/* SetCriterion.loss_boxes (model/box_utils.py:157-173) on matched pairs: pair k = (pred[src_row[k]], tgt[k]), boxes in
+ * cxcywh.  losses[0] = sum |p - t| / num_boxes, losses[1] = sum (1 - GIoU(p, t)) / num_boxes (GIoU as in
+ * utils/box_ops.py:24-61).  backward: grad_pred [pred_rows, 4] (zero-filled, then one row per pair) for upstream
+ * gradients g_losses[0..1]; follows the eager reference's autograd conventions (ties of max/min split 0.5/0.5). */
+int hh_box_loss_forward(const float* pred, const int64_t* src_row, const float* tgt, int K, float num_boxes,
+                        float* losses, void* stream);
+int hh_box_loss_backward(const float* pred, const int64_t* src_row, const float* tgt, int K, float num_boxes,
+                         const float* g_losses, float* grad_pred, int64_t pred_rows, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Assignment: the per-image / per-clip scipy.optimize.linear_sum_assignment calls of HungarianMatcher.forward
  * (model/box_utils.py:89-92) and WordContrastiveLoss.forward (model/loss.py:88-93), batched on the device.

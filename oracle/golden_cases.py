@@ -117,8 +117,17 @@ def make_inputs(case):
         pl = torch.randn(c["bs"], c["nq"], c["ncls"], generator=g)
         tb = [rb(k) for k in c["sizes"]]
         tl = [torch.randint(0, c["ncls"], (k,), generator=g) for k in c["sizes"]]
+        # compute_box_loss inputs: 8 frames x 12 queries (2 hand + 10 object), pixel xyxy targets [frames, 4, 4] with
+        # absent (all-zero) and degenerate rows; drawn last so the tensors above keep their values
+        det_boxes = rb(8 * 12).view(8, 12, 4)
+        det_logits = torch.randn(8, 12, c["ncls"], generator=g)
+        lo = 224 * torch.rand(8, 4, 2, generator=g) * 0.7
+        px = torch.cat([lo, lo + 10 + 60 * torch.rand(8, 4, 2, generator=g)], -1)
+        px[torch.rand(8, 4, generator=g) < 0.3] = 0.0
+        px[1, 0] = torch.tensor([50., 60., 50., 90.])        # zero width: dropped by prepare_targets
+        px[2, :2] = 0.0                                        # a frame without hands
         return dict(vid=vid, txt=txt, verb=verb, noun=noun, pad=pad, nouns=nouns, pred=pred, inds=inds, pred_boxes=pb,
-                    pred_logits=pl, tgt_boxes=tb, tgt_labels=tl)
+                    pred_logits=pl, tgt_boxes=tb, tgt_labels=tl, det_boxes=det_boxes, det_logits=det_logits, det_px=px)
     if kind == "score":
         a = torch.randn(case["Na"], case["d"], generator=g)
         b = torch.randn(case["Nb"], case["d"], generator=g)
@@ -131,11 +140,12 @@ def make_inputs(case):
     raise ValueError(kind)
 
 
-def run_losses(inp, sim_matrix, egonce, word_loss, matcher):
+def run_losses(inp, sim_matrix, egonce, word_loss, matcher, box_loss):
     """Shared driver of the 'losses' case: the same sequence of calls is made with the reference's modules
     (make_golden.py), the oracle's restatements (run_oracle) and the CUDA mirrors (tests/test_gpu_losses.py).
     egonce(x, mask_v, mask_n, pad) -> (loss, mask_bool); word_loss(nouns, pred, inds) -> (loss, flat col indices);
-    matcher(outputs, targets, exclude_class) -> [(i, j)]."""
+    matcher(outputs, targets, exclude_class) -> [(i, j)]; box_loss(detr_out, pixel_boxes, box_type) -> (loss, [(i, j)])
+    = compute_box_loss(box_type, criterion, detr_out, boxes, None, sizes, n_queries=12)."""
     res = {}
     vid = inp["vid"].clone().requires_grad_(True)
     txt = inp["txt"].clone().requires_grad_(True)
@@ -165,6 +175,18 @@ def run_losses(inp, sim_matrix, egonce, word_loss, matcher):
         res[name + "_i"] = torch.cat([i for i, _ in idx])
         res[name + "_j"] = torch.cat([j for _, j in idx])
         res[name + "_n"] = torch.tensor([len(i) for i, _ in idx])
+    det = inp["det_boxes"].clone().requires_grad_(True)
+    detr_out = {"pred_boxes": det, "pred_logits": inp["det_logits"],
+                "aux_outputs": [{"pred_boxes": det.detach(), "pred_logits": inp["det_logits"]}]}
+    total = 0
+    for box_type, sl in (("hand_boxes", slice(0, 2)), ("obj_boxes", slice(2, 4))):
+        loss, idx = box_loss(detr_out, inp["det_px"][:, sl].clone(), box_type)
+        total = total + loss
+        res["box_" + box_type] = loss.detach()
+        res["box_" + box_type + "_i"] = torch.cat([i for i, _ in idx])
+        res["box_" + box_type + "_j"] = torch.cat([j for _, j in idx])
+    total.backward()
+    res["box_dpred"] = det.grad.clone()
     return res
 
 
@@ -194,8 +216,11 @@ def run_oracle(case):
             if excl:
                 return O.hungarian_match(outputs["pred_boxes"], tb)
             return O.hungarian_match(outputs["pred_boxes"], tb, outputs["pred_logits"], tl)
+        def box(detr_out, px, box_type):
+            start, end = (0, 2) if box_type == "hand_boxes" else (2, 12)
+            return O.box_loss(detr_out["pred_boxes"], px, start, end)
         return run_losses(make_inputs(case), O.sim_matrix,
-                          lambda x, mv, mn, pad: O.egonce_loss(x, mv, mn, pad), word, matcher)
+                          lambda x, mv, mn, pad: O.egonce_loss(x, mv, mn, pad), word, matcher, box)
     with torch.no_grad():
         if kind == "encoder":
             c = case["cfg"]

@@ -568,3 +568,30 @@ def calculate_nDCG(similarity_matrix, relevancy_matrix, k_counts=None, IDCG=None
     if IDCG is None:
         IDCG = calculate_DCG(relevancy_matrix, relevancy_matrix, k_counts)
     return np.mean(dcg / IDCG), dcg / IDCG
+
+
+def prepare_targets(boxes: Tensor, center_crop_224: bool = True) -> List[Dict[str, Tensor]]:
+    """prepare_targets(..., classes=None, center_crop=False) (model/box_utils.py:249-279): pixel xyxy boxes clipped to
+    [0, 224] and normalised; all-zero / degenerate boxes dropped; labels = 1 - (box.sum != 0) (dummy, unused)."""
+    labels = 1 - (boxes.sum(-1) != 0).float()
+    b = torch.clip(boxes, min=0, max=224).div(224)
+    out = []
+    for c_, b_ in zip(labels, b):
+        ok = (c_ != -1) * (b_[:, 2] > b_[:, 0]) * (b_[:, 3] > b_[:, 1])
+        out.append({"labels": c_[ok], "boxes": box_xyxy_to_cxcywh(b_[ok])})
+    return out
+
+
+def box_loss(pred_boxes: Tensor, target_px: Tensor, start: int, end: int, w_bbox: float = 5.0, w_giou: float = 2.0):
+    """compute_box_loss (model/box_utils.py:446-461) for one query range: split_detr_out [start, end), Hungarian matching
+    with exclude_class=True, SetCriterion.loss_boxes (:157-173) = L1 / num_boxes and (1 - diag GIoU) / num_boxes, weighted
+    5 / 2 and divided by len(weight_dict) / 3 = 4 / 3 (run/train.py:460-463)."""
+    targets = prepare_targets(target_px)
+    pred = pred_boxes[:, start:end]
+    idx = hungarian_match(pred.detach(), [t["boxes"] for t in targets])
+    num_boxes = max(float(sum(len(t["labels"]) for t in targets)), 1.0)
+    src = torch.cat([pred[i, s] for i, (s, _) in enumerate(idx)])
+    tgt = torch.cat([t["boxes"][j] for t, (_, j) in zip(targets, idx)])
+    l1 = (src - tgt).abs().sum() / num_boxes
+    giou = (1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tgt)))).sum() / num_boxes
+    return (w_bbox * l1 + w_giou * giou) / (4 / 3), idx

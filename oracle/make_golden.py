@@ -41,9 +41,21 @@ def run_reference(case):
                     cost = -ns.metric.sim_matrix(nouns[ids], pred[b]).detach()
                     cols.append(torch.as_tensor(linear_sum_assignment(cost)[1], dtype=torch.int64))
             return wl(nouns, pred, inds), torch.cat(cols)
+        crit = box_utils.SetCriterion(22047, matcher=m, eos_coef=0.1, losses=["boxes", "cardinality"],
+                                      weight_dict={"loss_bbox_hand_boxes": 5, "loss_bbox_obj_boxes": 5,
+                                                   "loss_giou_hand_boxes": 2, "loss_giou_obj_boxes": 2})   # run/train.py:460-472
+
+        def box(detr_out, px, box_type):
+            sizes = torch.full((px.shape[0], 2), 224.0)
+            keep = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self      # prepare_targets hard-codes .cuda() (model/box_utils.py:255)
+            try:
+                return box_utils.compute_box_loss(box_type, crit, detr_out, px, None, sizes, n_queries=12)
+            finally:
+                torch.Tensor.cuda = keep
         return gc.run_losses(gc.make_inputs(case), ns.metric.sim_matrix,
                              lambda x, mv, mn, pad: nce(x, mv, mn, multi_pad_mask=pad, strict_mask=True), word,
-                             lambda o, t, e: m(o, t, exclude_class=e))
+                             lambda o, t, e: m(o, t, exclude_class=e), box)
     with torch.no_grad():
         if kind == "encoder":
             c = case["cfg"]

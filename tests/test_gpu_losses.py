@@ -41,8 +41,15 @@ def _cuda_losses(inp):
 
     def matcher(outputs, targets, excl):
         return m(outputs, targets, exclude_class=excl)
+    crit = box_utils.SetCriterion(22047, matcher=m, eos_coef=0.1, losses=["boxes", "cardinality"],
+                                  weight_dict={"loss_bbox_hand_boxes": 5, "loss_bbox_obj_boxes": 5,
+                                               "loss_giou_hand_boxes": 2, "loss_giou_obj_boxes": 2}).cuda()
+
+    def box(detr_out, px, box_type):
+        sizes = torch.full((px.shape[0], 2), 224.0, device=px.device)
+        return box_utils.compute_box_loss(box_type, crit, detr_out, px, None, sizes, n_queries=12)
     res = gc.run_losses(dev, metric.sim_matrix, lambda x, mv, mn, pad: nce(x, mv, mn, multi_pad_mask=pad, strict_mask=True),
-                        word, matcher)
+                        word, matcher, box)
     return {k: v.cpu() for k, v in res.items()}
 
 
