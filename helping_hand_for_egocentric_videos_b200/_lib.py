@@ -66,6 +66,10 @@ SIGNATURES = {
     "hh_word_loss_forward": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "hh_word_loss_backward": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hh_retrieval_rows": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "hh_linear_f32_backward": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _f, _p]),
+    "hh_layernorm_backward": (_i, [_p, _i, _p, _f, _p, _i, _p, _p, _p, _i, _i, _p]),
+    "hh_self_attention_backward": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "hh_cross_attention_backward": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "hh_attention_causal": (_i, [_p, _p, _i, _i, _i, _p]),
     "hh_profile_num_classes": (_i, []),
     "hh_profile_class_name": (C.c_char_p, [_i]),

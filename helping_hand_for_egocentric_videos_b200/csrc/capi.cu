@@ -250,6 +250,48 @@ int hh_retrieval_rows(const double* sim, const double* rel, const double* logs, 
   return retrieval_rows(sim, rel, logs, kcounts, N, M, mode, out, S(stream));
 }
 
+// ------------------------------------------------------------------------------------------ decoder backward primitives
+int hh_linear_f32_backward(const float* dY, int ldy, const float* Y, int ldyo, int act, const float* W, const float* X,
+                           int ldx, const float* x_add, int add_mod, int in_relu, float* dX, int lddx, float* dW,
+                           float* db, int R, int N, int K, float beta, float scale, void* stream) {
+  LinBwdArgs a{};
+  a.dY = dY; a.ldy = ldy; a.Y = Y; a.ldyo = ldyo; a.act = act; a.W = W; a.X = X; a.ldx = ldx; a.x_add = x_add;
+  a.add_mod = add_mod; a.in_relu = in_relu; a.dX = dX; a.lddx = lddx; a.dW = dW; a.ldw = K; a.db = db; a.R = R; a.N = N;
+  a.K = K; a.beta = beta; a.scale = scale;
+  if (dX) {
+    int rc = linear_dgrad_f32(a, S(stream));
+    if (rc) return rc;
+  }
+  if (dW) return linear_wgrad_f32(a, S(stream));
+  return 0;
+}
+int hh_layernorm_backward(const float* x, int ldx, const float* w, float eps, const float* dy, int lddy, float* dx,
+                          float* dgamma, float* dbeta, int M, int D, void* stream) {
+  HH_GUARD_BEGIN
+  static thread_local DevBuf ws;
+  int rc = ws.reserve(ln_backward_workspace_bytes(M, D));
+  if (rc) return rc;
+  LnBwdArgs a{};
+  a.x = x; a.ldx = ldx; a.w = w; a.eps = eps; a.dy = dy; a.lddy = lddy; a.dx = dx; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.workspace = ws.ptr; a.M = M; a.D = D;
+  return ln_backward_rows(a, S(stream));
+  HH_GUARD_END
+}
+int hh_self_attention_backward(const float* q, const float* k, const float* v, int ld, const float* dO, float* dq,
+                               float* dk, float* dv, int ldg, int B, int Q, int heads, void* stream) {
+  return self_attn_bwd(q, k, v, ld, dO, dq, dk, dv, ldg, B, Q, heads, S(stream));
+}
+int hh_cross_attention_backward(const float* q, const void* K, const void* V, int ldkv, const float* O, const float* dO,
+                                float* dq, void* dK, void* dV, int lddkv, int B, int Q, int heads, int S_, void* stream) {
+  HH_GUARD_BEGIN
+  static thread_local DevBuf ws;
+  int rc = ws.reserve(cross_attn_bwd_workspace_bytes(B, Q, heads, S_));
+  if (rc) return rc;
+  return cross_attn_bwd(q, static_cast<const bf16*>(K), static_cast<const bf16*>(V), ldkv, O, dO, dq,
+                        static_cast<bf16*>(dK), static_cast<bf16*>(dV), lddkv, B, Q, heads, S_, ws.ptr, S(stream));
+  HH_GUARD_END
+}
+
 // ------------------------------------------------------------------------------------------ kernel-level entry points
 int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
                  const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream) {

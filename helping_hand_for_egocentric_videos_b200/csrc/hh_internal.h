@@ -136,6 +136,51 @@ int build_pos3d(const float* pos_embed, const float* temporal, float* out, int T
 int l2_normalize_rows(const float* x, float* out, int rows, int cols, float eps, cudaStream_t stream);
 int expand_logits(const float* src, float* dst, int LB, int rep, size_t per, cudaStream_t stream);
 
+// ---------------------------------------------------------------- decoder backward primitives (decoder_bwd.cu)
+// nn.Linear backward.  g = act'(dY, Y) (act 0 none, 1 relu, 2 sigmoid; Y = saved output).
+//   dgrad: dX[R,K] = beta*dX + g W           (W fp32 [N,K])
+//   wgrad: dW[N,K] = beta*dW + scale * g^T x,  x = relu?(X + x_add[r % add_mod]);  db[N] = beta*db + scale * sum_r g
+struct LinBwdArgs {
+  const float* dY; int ldy;
+  const float* Y; int ldyo; int act;
+  const float* W;
+  const float* X; int ldx;
+  const float* x_add; int add_mod; int in_relu;
+  float* dX; int lddx;  // dgrad output
+  float* dW; int ldw;   // wgrad outputs
+  float* db;
+  int R, N, K;
+  float beta, scale;
+};
+int linear_dgrad_f32(const LinBwdArgs& a, cudaStream_t s);
+int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s);
+// LayerNorm backward over rows of x (+ optional bf16 delta, as in the forward).  dy fp32 or bf16 (row stride lddy).
+// dx = beta_dx * dx + grad (fp32, contiguous rows) and/or dx16 (bf16);  dgamma/dbeta = beta_w * old + sum over rows.
+struct LnBwdArgs {
+  const float* x; int ldx; const bf16* delta;
+  const float* w; float eps;
+  const float* dy; const bf16* dy16; int lddy;
+  float* dx; bf16* dx16; float beta_dx;
+  float* dgamma; float* dbeta; float beta_w;
+  void* workspace;  // ln_backward_workspace_bytes(M, D) when dgamma is requested
+  int M, D;
+};
+size_t ln_backward_workspace_bytes(int M, int D);
+int ln_backward_rows(const LnBwdArgs& a, cudaStream_t s);
+// backward of self_attn_queries: dq/dk/dv rows have stride ldg (same packing as the forward's q/k/v with stride ld)
+int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const float* dO, float* dq, float* dk, float* dv,
+                  int ldg, int B, int Q, int heads, cudaStream_t s);
+// backward of cross_attn: dq fp32 [B*Q, C]; dK, dV bf16 rows [B*S] with stride lddkv (head h at column h*64)
+size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S);
+int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
+                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s);
+// out[c] = beta*out[c] + sum_r X[r, c]  (X fp32 or bf16, row stride ld); workspace colsum_workspace_bytes(cols)
+size_t colsum_workspace_bytes(long long cols);
+int colsum_rows(const void* X, int is_bf16, long long ld, long long rows, long long cols, float beta, float* out,
+                void* workspace, cudaStream_t s);
+// out bf16 [cols, rows] = transpose(in [rows, cols]) (in fp32 or bf16, row stride ld)
+int transpose_to_bf16(const void* in, int is_bf16, long long ld, bf16* out, long long rows, long long cols, cudaStream_t s);
+
 // ---------------------------------------------------------------- scoring / boxes (score.cu, box.cu)
 int sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, cudaStream_t stream);
 // mode 0: argmax over columns -> int64 ; 1: row softmax(x*scale) ; 2: row log_softmax(x*scale)

@@ -249,3 +249,51 @@ def retrieval_rows(sim, rel, mode: int, kcounts=None):
     L.check(L.load().hh_retrieval_rows(L.ptr(s), L.ptr(r), L.ptr(logs), L.ptr(kc), N, M, mode, L.ptr(out),
                                        L.stream_ptr()), "hh_retrieval_rows")
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ backward primitives
+def linear_f32_backward(dy, y, act, weight, x, x_add=None, in_relu=False, need_dx=True, need_dw=True):
+    """Backward of linear_f32: returns (dx, dw, db)."""
+    dy, weight, x = _f32(dy), _f32(weight), _f32(x)
+    R, N = dy.shape
+    K = weight.shape[1]
+    dx = torch.empty(R, K, dtype=torch.float32, device=dy.device) if need_dx else None
+    dw = torch.empty(N, K, dtype=torch.float32, device=dy.device) if need_dw else None
+    db = torch.empty(N, dtype=torch.float32, device=dy.device) if need_dw else None
+    yy = _f32(y) if act else None
+    xa = _f32(x_add) if x_add is not None else None
+    L.check(L.load().hh_linear_f32_backward(L.ptr(dy), N, L.ptr(yy), N, act, L.ptr(weight), L.ptr(x), K, L.ptr(xa),
+                                            xa.shape[0] if xa is not None else 0, 1 if in_relu else 0, L.ptr(dx), K,
+                                            L.ptr(dw), L.ptr(db), R, N, K, 0.0, 1.0, L.stream_ptr()),
+            "hh_linear_f32_backward")
+    return dx, dw, db
+
+
+def layernorm_backward(x, w, dy, eps):
+    x, w, dy = _f32(x), _f32(w), _f32(dy)
+    M, D = x.shape
+    dx, dg, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(w)
+    L.check(L.load().hh_layernorm_backward(L.ptr(x), D, L.ptr(w), eps, L.ptr(dy), D, L.ptr(dx), L.ptr(dg), L.ptr(db), M, D,
+                                           L.stream_ptr()), "hh_layernorm_backward")
+    return dx, dg, db
+
+
+def self_attention_backward(qkv, dO, B, Q, heads):
+    """qkv fp32 [B*Q, 3C] packed (q pre-scaled) -> d(qkv) in the same packing."""
+    qkv, dO = _f32(qkv), _f32(dO)
+    Cc = heads * 64
+    g = torch.empty_like(qkv)
+    p, pg = L.ptr(qkv), L.ptr(g)
+    L.check(L.load().hh_self_attention_backward(p, p + 4 * Cc, p + 8 * Cc, 3 * Cc, L.ptr(dO), pg, pg + 4 * Cc, pg + 8 * Cc,
+                                                3 * Cc, B, Q, heads, L.stream_ptr()), "hh_self_attention_backward")
+    return g
+
+
+def cross_attention_backward(q, K, V, O, dO, B, Q, heads, S):
+    q, O, dO = _f32(q), _f32(O), _f32(dO)
+    dq = torch.empty_like(q)
+    dK, dV = torch.empty_like(K), torch.empty_like(V)
+    L.check(L.load().hh_cross_attention_backward(L.ptr(q), L.ptr(K), L.ptr(V), K.shape[1], L.ptr(O), L.ptr(dO), L.ptr(dq),
+                                                 L.ptr(dK), L.ptr(dV), dK.shape[1], B, Q, heads, S, L.stream_ptr()),
+            "hh_cross_attention_backward")
+    return dq, dK, dV

@@ -253,6 +253,28 @@ int hh_retrieval_rows(const double* sim, const double* rel, const double* logs, 
                       int mode, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Decoder backward primitives (kernel-level entry points; the decoder engine sequences them in hh_decoder_backward).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* nn.Linear backward for y = act(x W^T + b), x = relu?(X + x_add[r % add_mod]).  g = act'(dY, Y) with Y the saved output
+ * (act 0 none / 1 relu / 2 sigmoid).  dX [R,K] = beta*dX + g W (skipped when NULL); dW [N,K] = beta*dW + scale * g^T x and
+ * db [N] = beta*db + scale * colsum(g) (skipped when dW is NULL; db may be NULL). */
+int hh_linear_f32_backward(const float* dY, int ldy, const float* Y, int ldyo, int act, const float* W, const float* X,
+                           int ldx, const float* x_add, int add_mod, int in_relu, float* dX, int lddx, float* dW,
+                           float* db, int R, int N, int K, float beta, float scale, void* stream);
+/* LayerNorm backward over M rows of width D (multiple of 128, <= 1024): dx (overwritten), dgamma / dbeta (overwritten;
+ * both or neither). */
+int hh_layernorm_backward(const float* x, int ldx, const float* w, float eps, const float* dy, int lddy, float* dx,
+                          float* dgamma, float* dbeta, int M, int D, void* stream);
+/* Backward of the query self-attention core (hh_decoder's self_attn): q,k,v fp32 rows with stride ld (q pre-scaled),
+ * dO fp32 [B*Q, heads*64] -> dq, dk, dv rows with stride ldg. */
+int hh_self_attention_backward(const float* q, const float* k, const float* v, int ld, const float* dO, float* dq,
+                               float* dk, float* dv, int ldg, int B, int Q, int heads, void* stream);
+/* Backward of hh_cross_attention: O = forward output, dO its gradient (fp32 [B*Q, heads*64]) -> dq fp32 [B*Q, heads*64],
+ * dK / dV bf16 rows [B*S] with stride lddkv. */
+int hh_cross_attention_backward(const float* q, const void* K, const void* V, int ldkv, const float* O, const float* dO,
+                                float* dq, void* dK, void* dV, int lddkv, int B, int Q, int heads, int S, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Data-parallel exchange: the one collective of the path (all-gather of embeddings for the cross-rank similarity
  * matrix, run/train.py:36-37,126-128; _valid_all_gather, utils/train_utils.py:51-59).  NCCL is resolved at run time
  * (dlopen of the libnccl.so.2 already loaded by the host framework); one communicator per process / GPU.
