@@ -99,6 +99,32 @@ int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b,
   return dec->impl.forward(features, stride_b, stride_row, B, T, hs, logits, boxes, S(stream));
   HH_GUARD_END
 }
+int hh_decoder_forward_train(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
+                             float* hs, float* logits, float* boxes, void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_forward_train: null handle");
+  return dec->impl.forward(features, stride_b, stride_row, B, T, hs, logits, boxes, S(stream), true);
+  HH_GUARD_END
+}
+int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, const float* d_hs, const float* d_boxes,
+                        void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_backward: null handle");
+  return dec->impl.backward(hs, boxes, d_hs, d_boxes, S(stream));
+  HH_GUARD_END
+}
+int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec || !key || !out) return fail(-2, "hh_decoder_get_grad: null argument");
+  auto it = dec->impl.weights.expected.find(key);
+  if (it == dec->impl.weights.expected.end()) return fail(-2, std::string("unknown parameter key '") + key + "'");
+  if (it->second != numel) return fail(-2, std::string("parameter '") + key + "': wrong element count");
+  const float* g = dec->impl.grad(key);
+  if (!g) return fail(-2, "hh_decoder_get_grad: no gradient yet (run hh_decoder_backward)");
+  HH_CHECK_CUDA(cudaMemcpyAsync(out, g, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, S(stream)));
+  return 0;
+  HH_GUARD_END
+}
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T) { return dec ? dec->impl.flops_per_clip(T) : 0.0; }
 int hh_decoder_last_launches(const hh_decoder* dec) { return dec ? dec->impl.launches : 0; }
 

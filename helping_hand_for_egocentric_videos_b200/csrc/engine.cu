@@ -409,6 +409,11 @@ int Decoder::pack(cudaStream_t s) {
     RC(scale_copy_f32(weights.get(p + "self_attn.in_proj_bias"), static_cast<float*>(b_sa.ptr) + static_cast<size_t>(i) * 3 * C,
                       3 * C, C, qscale, s));
   }
+  // K-major copies of the K / V projection weights for the data-gradient GEMMs of backward(): [C, L*C]
+  RC(w_kallT.reserve(static_cast<size_t>(Lr) * C * C * 2));
+  RC(w_vallT.reserve(static_cast<size_t>(Lr) * C * C * 2));
+  RC(transpose_to_bf16(w_kall.ptr, 1, C, static_cast<bf16*>(w_kallT.ptr), static_cast<long long>(Lr) * C, C, s));
+  RC(transpose_to_bf16(w_vall.ptr, 1, C, static_cast<bf16*>(w_vallT.ptr), static_cast<long long>(Lr) * C, C, s));
   // constant 3-D position embedding (tfm_decoder.py:161-166)
   const int S = cfg.num_frames * cfg.patches_per_frame;
   RC(pos3d.reserve(static_cast<size_t>(S) * C * 4));
@@ -446,7 +451,7 @@ static int lin(const float* in, int ldi, const float* in_add, int add_mod, const
 }
 
 int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row, int B, int T, float* hs, float* logits,
-                     float* boxes, cudaStream_t s) {
+                     float* boxes, cudaStream_t s, bool save) {
   HH_REQUIRE(B > 0 && features && hs && logits && boxes, "decoder forward: bad arguments");
   HH_REQUIRE(T == cfg.num_frames, "decoder forward: T must equal num_frames (construct_3d_pos_embed, tfm_decoder.py:161-166)");
   if (weights.dirty) RC(pack(s));
@@ -475,11 +480,34 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   bf16* Kall = static_cast<bf16*>(ws_k.ptr);
   bf16* Vall = static_cast<bf16*>(ws_v.ptr);
   float* tgt = static_cast<float*>(ws_q.ptr);
-  float* t2 = tgt + static_cast<size_t>(R) * C;
-  float* o = t2 + static_cast<size_t>(R) * C;
-  float* qkv = o + static_cast<size_t>(R) * C;
-  float* ffn = qkv + static_cast<size_t>(R) * 3 * C;
   const float* qpos = weights.get("query_embed.weight");
+  // per-layer activation buffers: one shared set in inference, one set per layer when saving for backward()
+  saved.assign(Lr, LayerBufs{});
+  {
+    const size_t RC_ = static_cast<size_t>(R) * C;
+    if (!save) {
+      float* t2 = tgt + RC_;
+      float* o = t2 + RC_;
+      float* qkv = o + RC_;
+      float* ffn = qkv + 3 * RC_;
+      for (auto& b : saved) b = LayerBufs{tgt, tgt, tgt, tgt, t2, t2, t2, qkv, o, qkv, o, ffn};
+      saved_B = 0;
+    } else {
+      const size_t per = 12 * RC_ + static_cast<size_t>(R) * Fd;  // x0,x1,x2,n1,n2,n3 (6) qkv (3) o1,qc,o2 (3) + f
+      RC(ws_train.reserve((per * Lr + RC_) * 4));
+      float* p0 = static_cast<float*>(ws_train.ptr);
+      for (int i = 0; i < Lr; ++i) {
+        float* b = p0 + per * i;
+        LayerBufs& L = saved[i];
+        L.x0 = b; L.x1 = b + RC_; L.x2 = b + 2 * RC_; L.n1 = b + 3 * RC_; L.n2 = b + 4 * RC_; L.n3 = b + 5 * RC_;
+        L.qkv = b + 6 * RC_; L.o1 = b + 9 * RC_; L.qc = b + 10 * RC_; L.o2 = b + 11 * RC_; L.f = b + 12 * RC_;
+        L.x3 = (i + 1 < Lr) ? p0 + per * (i + 1) : p0 + per * Lr;  // = x0 of the next layer
+      }
+      tgt = saved[0].x0;
+      saved_B = B;
+      saved_T = T;
+    }
+  }
 
   // proj (no bias, :200) -> pre_norm (:86) ; memory and memory+pos in bf16 for the K/V GEMMs
   PROF(K_DEC_GEMM, cast_rows_bf16(features, stride_b, stride_row, S, feat, static_cast<int>(BS), F, s));
@@ -509,29 +537,30 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
     const std::string p = "transformer.decoder.layers." + std::to_string(i) + ".";
     const float* wsa = static_cast<const float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C;
     const float* bsa = static_cast<const float*>(b_sa.ptr) + static_cast<size_t>(i) * 3 * C;
+    const LayerBufs& A = saved[i];
     // self attention over the queries (:431-435)
-    PROF(K_DEC_QUERY, lnq(tgt, p + "norm1", t2));
-    PROF(K_DEC_QUERY, lin(t2, C, qpos, Q, wsa, bsa, nullptr, 0, qkv, 3 * C, R, 2 * C, C, 0, s));                       // q,k <- t2+qpos
-    PROF(K_DEC_QUERY, lin(t2, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, qkv + 2 * C, 3 * C, R, C, C, 0, s));
-    PROF(K_DEC_QUERY, self_attn_queries(qkv, qkv + C, qkv + 2 * C, 3 * C, o, B, Q, heads, s));
-    PROF(K_DEC_QUERY, lin(o, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), tgt, C,
-           tgt, C, R, C, C, 0, s));
+    PROF(K_DEC_QUERY, lnq(A.x0, p + "norm1", A.n1));
+    PROF(K_DEC_QUERY, lin(A.n1, C, qpos, Q, wsa, bsa, nullptr, 0, A.qkv, 3 * C, R, 2 * C, C, 0, s));                   // q,k <- n1+qpos
+    PROF(K_DEC_QUERY, lin(A.n1, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, A.qkv + 2 * C, 3 * C, R, C, C, 0, s));
+    PROF(K_DEC_QUERY, self_attn_queries(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, A.o1, B, Q, heads, s));
+    PROF(K_DEC_QUERY, lin(A.o1, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), A.x0, C,
+           A.x1, C, R, C, C, 0, s));
     // cross attention to the patch tokens (:436-441,456)
-    PROF(K_DEC_QUERY, lnq(tgt, p + "norm2", t2));
-    PROF(K_DEC_QUERY, lin(t2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
-           static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, qkv, C, R, C, C, 0, s));
-    PROF(K_DEC_CROSS, cross_attn(qkv, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, o, B, Q, heads, S,
+    PROF(K_DEC_QUERY, lnq(A.x1, p + "norm2", A.n2));
+    PROF(K_DEC_QUERY, lin(A.n2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
+           static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, A.qc, C, R, C, C, 0, s));
+    PROF(K_DEC_CROSS, cross_attn(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, B, Q, heads, S,
                   ws_cross.ptr, s));
-    PROF(K_DEC_QUERY, lin(o, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
-           tgt, C, tgt, C, R, C, C, 0, s));
+    PROF(K_DEC_QUERY, lin(A.o2, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
+           A.x1, C, A.x2, C, R, C, C, 0, s));
     // FFN (:457-459)
-    PROF(K_DEC_QUERY, lnq(tgt, p + "norm3", t2));
-    PROF(K_DEC_QUERY, lin(t2, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, ffn, Fd, R, Fd, C,
+    PROF(K_DEC_QUERY, lnq(A.x2, p + "norm3", A.n3));
+    PROF(K_DEC_QUERY, lin(A.n3, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, A.f, Fd, R, Fd, C,
            1, s));
-    PROF(K_DEC_QUERY, lin(ffn, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), tgt, C, tgt, C, R, C, Fd, 0,
+    PROF(K_DEC_QUERY, lin(A.f, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), A.x2, C, A.x3, C, R, C, Fd, 0,
            s));
     // intermediate output through the shared final norm (:282,287-291)
-    PROF(K_DEC_QUERY, lnq(tgt, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
+    PROF(K_DEC_QUERY, lnq(A.x3, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
     launches += 15;
   }
 
@@ -549,6 +578,7 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   float* x2 = reinterpret_cast<float*>(hp);
   hp += rows_box * C * 4;
   float* logits_raw = traj ? reinterpret_cast<float*>(hp) : logits;
+  sv_cond = cond; sv_x1 = x1; sv_x2 = x2; sv_hsproj = hsproj;
 
   PROF(K_DEC_HEADS, f32_to_bf16(hs, hs16, LR * C, s));
   PROF(K_DEC_HEADS, gemm_bf16(hs16, C, static_cast<const bf16*>(w_cls.ptr), C, logits_raw, ncls, weights.get("class_embed.bias"), nullptr, 0,

@@ -88,11 +88,31 @@ struct Decoder {
   DevBuf w_proj, w_cls, w_kall, w_vall, b_kall, b_vall, w_sa, b_sa, w_caq, b_caq, pos3d, w_f1, w_f2, frameterm;
   DevBuf ws_feat, ws_memf, ws_mem, ws_mempos, ws_k, ws_v, ws_q, ws_cross, ws_head;
 
+  // ---- training state (engine_bwd.cu): activations of the last forward(save = true) and the parameter gradients
+  struct LayerBufs {  // fp32 [B*Q, .] each; in inference mode every layer aliases one set
+    float *x0, *x1, *x2, *x3;   // residual stream before norm1 / norm2 / norm3 / after the FFN
+    float *n1, *n2, *n3;        // LayerNorm outputs
+    float *qkv, *o1;            // self-attention packed projections (q pre-scaled) and core output
+    float *qc, *o2;             // cross-attention query projection (pre-scaled) and core output
+    float* f;                   // FFN hidden after ReLU
+  };
+  std::vector<LayerBufs> saved;
+  int saved_B = 0, saved_T = 0;
+  float *sv_cond = nullptr, *sv_x1 = nullptr, *sv_x2 = nullptr, *sv_hsproj = nullptr;
+  DevBuf ws_train, w_kallT, w_vallT;
+  DevBuf bw_a, bw_b, bw_c, bw_d, bw_dk, bw_dv, bw_t1, bw_t2, bw_t3, bw_ws;
+  std::map<std::string, DevBuf> grads;
+
   explicit Decoder(const hh_decoder_cfg& c);
   static int validate(const hh_decoder_cfg& c);
   int pack(cudaStream_t s);
+  // save = true keeps every layer's activations for backward() (training forward; eval-mode arithmetic, no dropout)
   int forward(const float* features, int64_t stride_b, int64_t stride_row, int B, int T, float* hs, float* logits,
-              float* boxes, cudaStream_t s);
+              float* boxes, cudaStream_t s, bool save = false);
+  // Gradients of all decoder parameters for upstream d_hs [L,B,Q,C] and d_boxes [L,B*Tb,Q,4] (either may be null = 0);
+  // hs / boxes are the outputs of the matching forward(save = true).  Results are read with grad().
+  int backward(const float* hs, const float* boxes, const float* d_hs, const float* d_boxes, cudaStream_t s);
+  const float* grad(const std::string& key) const;
   double flops_per_clip(int T) const;
 };
 

@@ -23,12 +23,39 @@ from .. import ops
 from .LaviLa import _ParamSync
 
 
+class _LinearFn(torch.autograd.Function):
+    """y = act(relu?(x) W^T + b) on hh_linear_f32 with the backward kernels of hh_linear_f32_backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, in_relu):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        x2 = x2 if (x2.dtype == torch.float32 and x2.is_contiguous()) else x2.float().contiguous()
+        y = ops.linear_f32(x2, weight.detach(), bias.detach() if bias is not None else None, act=act, in_relu=in_relu)
+        ctx.save_for_backward(x2, weight, y)
+        ctx.act, ctx.in_relu, ctx.shape, ctx.has_bias = act, in_relu, shp, bias is not None
+        return y.reshape(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, y = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        if need_dx and ctx.in_relu:
+            raise NotImplementedError("gradient through a leading ReLU of a native head is not implemented "
+                                      "(txt_proj's input comes from the frozen text tower)")
+        dy2 = dy.reshape(-1, weight.shape[0]).float().contiguous()
+        dx, dw, db = ops.linear_f32_backward(dy2, y, ctx.act, weight.detach().float().contiguous(), x2, None, ctx.in_relu,
+                                             need_dx=need_dx, need_dw=ctx.needs_input_grad[1])
+        return (dx.reshape(ctx.shape) if need_dx else None, dw, db if ctx.has_bias else None, None, None)
+
+
 class _NativeHead(nn.Sequential):
     """nn.Sequential of Linear / ReLU layers (same child indices => same state_dict keys as the reference's
-    nn.Sequential heads, tfm_decoder.py:168-180) evaluated with hh_linear_f32, ReLUs fused into the linears."""
+    nn.Sequential heads, tfm_decoder.py:168-180) evaluated with hh_linear_f32, ReLUs fused into the linears.  With
+    autograd enabled and trainable parameters, every linear records its hand-written backward."""
 
-    @torch.no_grad()
     def forward(self, x):
+        track = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         mods = list(self)
         pending_relu = False
         i = 0
@@ -40,13 +67,54 @@ class _NativeHead(nn.Sequential):
                 continue
             assert isinstance(m, nn.Linear)
             fuse_out = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
-            x = ops.linear_f32(x, m.weight.detach(), m.bias.detach() if m.bias is not None else None,
-                               act=1 if fuse_out else 0, in_relu=pending_relu)
+            if track:
+                x = _LinearFn.apply(x, m.weight, m.bias, 1 if fuse_out else 0, pending_relu)
+            else:
+                with torch.no_grad():
+                    x = ops.linear_f32(x, m.weight.detach(), m.bias.detach() if m.bias is not None else None,
+                                       act=1 if fuse_out else 0, in_relu=pending_relu)
             pending_relu = False
             i += 2 if fuse_out else 1
         if pending_relu:
             x = torch.relu(x)
         return x
+
+
+class _DecoderFn(torch.autograd.Function):
+    """ObjDecoder forward + hand-written backward (hh_decoder_forward_train / hh_decoder_backward).  The parameters are
+    passed as inputs only so that autograd routes their gradients; the arithmetic reads the engine's packed copies."""
+
+    @staticmethod
+    def forward(ctx, module, features, *params):
+        hs, logits, boxes = module._run_engine(features, train=True)
+        ctx.module = module
+        ctx.keys = [k for k, _ in module._engine_params()]
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(hs, boxes)
+        ctx.mark_non_differentiable(logits)
+        return hs, logits, boxes
+
+    @staticmethod
+    def backward(ctx, d_hs, d_logits, d_boxes):
+        hs, boxes = ctx.saved_tensors
+        m = ctx.module
+        lib = L.load()
+
+        def prep(g):
+            return None if g is None else (g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous())
+        d_hs, d_boxes = prep(d_hs), prep(d_boxes)
+        L.check(lib.hh_decoder_backward(m._engine(), L.ptr(hs), L.ptr(boxes), L.ptr(d_hs), L.ptr(d_boxes), L.stream_ptr()),
+                "hh_decoder_backward")
+        grads = []
+        for key, shp, need in zip(ctx.keys, ctx.shapes, ctx.needs_input_grad[2:]):
+            if not need:
+                grads.append(None)
+                continue
+            g = torch.empty(shp, dtype=torch.float32, device=hs.device)
+            L.check(lib.hh_decoder_get_grad(m._engine(), key.encode(), L.ptr(g), g.numel(), L.stream_ptr()),
+                    "hh_decoder_get_grad(%s)" % key)
+            grads.append(g)
+        return (None, None, *grads)
 
 
 class MLP(nn.Module):
@@ -217,34 +285,46 @@ class ObjDecoder(nn.Module):
         tile_temporal_embed = self.temporal_embed.repeat_interleave(self.patches_per_frame, 1)
         return (tile_pos_embed + tile_temporal_embed).view(1, T, self.patches_per_frame, self.pos_embed.shape[-1])
 
-    @torch.no_grad()
-    def forward(self, features, use_checkpoint=False):
-        """features [B,T,n,F] (fp32, any strides with a unit innermost stride) -> (out, hs, [], [])."""
-        if not features.is_cuda:
-            raise RuntimeError("ObjDecoder (B200): input is on %s; there is no CPU fallback" % features.device)
-        if self.training and self.transformer.dropout_p > 0 and not self._warned_train:
-            warnings.warn("ObjDecoder (B200) runs the inference forward: dropout is not applied and no autograd graph "
-                          "is recorded (decoder training is not part of this build yet)")
-            self._warned_train = True
+    def _run_engine(self, features, train: bool):
         B, T, n, F = features.shape
-        if n != self.patches_per_frame or F != self._cfg.feature_dim:
-            raise RuntimeError("expected features [B,T,%d,%d], got %s" % (self.patches_per_frame, self._cfg.feature_dim,
-                                                                          tuple(features.shape)))
-        if features.dtype != torch.float32:
-            features = features.float()
-        if features.stride(3) != 1 or features.stride(1) != n * features.stride(2) or features.stride(2) % 4 \
-                or features.stride(0) % 4 or features.data_ptr() % 16:
-            features = features.contiguous()
-        self.sync_weights()
         L_, Q, Cd, ncls = self._cfg.num_layers, self.num_queries, self.hidden_dim, self._cfg.num_classes1
         traj = self.pred_traj and T == self.num_frames
         dev = features.device
         hs = torch.empty(L_, B, Q, Cd, dtype=torch.float32, device=dev)
         logits = torch.empty(L_, B * (4 if traj else 1), Q, ncls, dtype=torch.float32, device=dev)
         boxes = torch.empty(L_, B * (T if traj else 1), Q, 4, dtype=torch.float32, device=dev)
-        L.check(L.load().hh_decoder_forward(self._engine(), features.data_ptr(), features.stride(0), features.stride(2),
-                                            B, T, L.ptr(hs), L.ptr(logits), L.ptr(boxes), L.stream_ptr()),
-                "hh_decoder_forward")
+        fn = L.load().hh_decoder_forward_train if train else L.load().hh_decoder_forward
+        L.check(fn(self._engine(), features.data_ptr(), features.stride(0), features.stride(2), B, T, L.ptr(hs),
+                   L.ptr(logits), L.ptr(boxes), L.stream_ptr()), "hh_decoder_forward")
+        return hs, logits, boxes
+
+    def forward(self, features, use_checkpoint=False):
+        """features [B,T,n,F] (fp32, any strides with a unit innermost stride) -> (out, hs, [], []).  With autograd
+        enabled and trainable parameters the engine keeps its activations and the outputs carry the hand-written
+        backward (gradients for every decoder parameter; `features` come from the frozen backbone and get none)."""
+        if not features.is_cuda:
+            raise RuntimeError("ObjDecoder (B200): input is on %s; there is no CPU fallback" % features.device)
+        if self.training and self.transformer.dropout_p > 0 and not self._warned_train:
+            warnings.warn("ObjDecoder (B200): dropout (p=%.2f in the reference's training mode) is not applied; the "
+                          "forward and its gradients are those of eval mode" % self.transformer.dropout_p)
+            self._warned_train = True
+        B, T, n, F = features.shape
+        if n != self.patches_per_frame or F != self._cfg.feature_dim:
+            raise RuntimeError("expected features [B,T,%d,%d], got %s" % (self.patches_per_frame, self._cfg.feature_dim,
+                                                                          tuple(features.shape)))
+        features = features.detach()
+        if features.dtype != torch.float32:
+            features = features.float()
+        if features.stride(3) != 1 or features.stride(1) != n * features.stride(2) or features.stride(2) % 4 \
+                or features.stride(0) % 4 or features.data_ptr() % 16:
+            features = features.contiguous()
+        self.sync_weights()
+        params = [p for _, p in self._engine_params()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            hs, logits, boxes = _DecoderFn.apply(self, features, *params)
+        else:
+            with torch.no_grad():
+                hs, logits, boxes = self._run_engine(features, train=False)
         out = {'pred_logits': logits[-1], 'pred_boxes': boxes[-1]}
         if self.aux_loss:
             out['aux_outputs'] = [{'pred_logits': a, 'pred_boxes': b} for a, b in zip(logits[:-1], boxes[:-1])]

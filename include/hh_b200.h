@@ -96,6 +96,17 @@ int hh_decoder_set_weight(hh_decoder* dec, const char* key, const float* data, i
  */
 int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
                        float* hs, float* logits, float* boxes, void* stream);
+/* Training: the same forward that also keeps every layer's activations inside the engine (eval-mode arithmetic: the
+ * reference's dropout 0.1, tfm_decoder.py:52, is not applied), then hh_decoder_backward differentiates it.
+ * hh_decoder_backward: hs / boxes are the outputs of that forward; d_hs [L,B,Q,C] and d_boxes [L,B*Tb,Q,4] are the
+ * upstream gradients (either may be NULL = zero).  Class logits carry no gradient (the reference criterion has no class
+ * loss, run/train.py:471, exclude_class=True): class_embed.* get zeros.  Gradients of every parameter key are then read
+ * with hh_decoder_get_grad (fp32, `numel` elements, device memory). */
+int hh_decoder_forward_train(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
+                             float* hs, float* logits, float* boxes, void* stream);
+int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, const float* d_hs, const float* d_boxes,
+                        void* stream);
+int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream);
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
 int hh_decoder_last_launches(const hh_decoder* dec);
 
