@@ -10,6 +10,7 @@ way the reference calls it, :456) the 22 048-way softmax the reference computes 
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -32,30 +33,28 @@ class HungarianMatcher(nn.Module):
             raise RuntimeError("HungarianMatcher (B200): pred_boxes is on %s; there is no CPU fallback" % boxes.device)
         bs, num_queries = logits.shape[:2]
         out_bbox = boxes.flatten(0, 1)
-        sizes = [len(v["boxes"]) for v in targets]
+        sizes = getattr(targets, "counts", None) or [len(v["boxes"]) for v in targets]
         assert len(sizes) == bs
         M = sum(sizes)
         if M == 0:
             e = torch.empty(0, dtype=torch.int64)
             return [(e.clone(), e.clone()) for _ in range(bs)]
-        tgt_bbox = torch.cat([v["boxes"] for v in targets]).to(out_bbox.device)
+        tgt_bbox = _packed(targets, "boxes").to(out_bbox.device)
         C = ops.box_match_cost(out_bbox, tgt_bbox, float(self.cost_bbox), float(self.cost_giou))    # [bs*Q, M]
         if not exclude_class:
-            tgt_ids = torch.cat([v["labels"] for v in targets]).to(out_bbox.device)
+            tgt_ids = _packed(targets, "labels").to(out_bbox.device)
             ops.match_cost_class(C, logits.flatten(0, 1), tgt_ids, float(self.cost_class))
-        starts = [0]
-        for s in sizes[:-1]:
-            starts.append(starts[-1] + s)
-        offset = [i * num_queries * M + starts[i] for i in range(bs)]
+        starts = np.concatenate([[0], np.cumsum(sizes[:-1])]).astype(np.int64)
+        offset = np.arange(bs, dtype=np.int64) * (num_queries * M) + starts
         ri, ci, cnt = ops.assign(C, offset, [M] * bs, [num_queries] * bs, sizes)
         K = ri.shape[1]
-        packed = torch.cat([ri, ci, cnt.to(torch.int64)[:, None]], dim=1).cpu()                      # one D2H
-        out = []
-        for i in range(bs):
-            k = int(packed[i, 2 * K])
-            if k < 0:
-                raise ValueError("cost matrix is infeasible")        # scipy's message for inf / nan costs
-            out.append((packed[i, :k].clone(), packed[i, K:K + k].clone()))
+        packed = torch.cat([ri, ci, cnt.to(torch.int64)[:, None]], dim=1).cpu().numpy()               # one D2H
+        counts = packed[:, 2 * K]
+        if (counts < 0).any():
+            raise ValueError("cost matrix is infeasible")            # scipy's message for inf / nan costs
+        out = [(torch.from_numpy(packed[i, :k]), torch.from_numpy(packed[i, K:K + k])) for i, k in enumerate(counts)]
+        # kept for SetCriterion.loss_boxes: lets it gather the matched pairs on the device without per-image indexing
+        self._last = (out, ri, ci, counts, starts, num_queries)
         return out
 
 
@@ -64,6 +63,17 @@ def build_matcher(args):
 
 
 # ---------------------------------------------------------------------------------------------- criterion
+class _PackedTargets(list):
+    """The per-image target dicts of prepare_targets plus the packed tensors they are views of, so the matcher and the
+    criterion need not concatenate them again."""
+    boxes = labels = counts = None
+
+
+def _packed(targets, key):
+    t = getattr(targets, key, None)
+    return t if t is not None else torch.cat([v[key] for v in targets])
+
+
 class _BoxLossFn(torch.autograd.Function):
     """(loss_bbox, loss_giou) of matched prediction / target pairs with the hand-written backward kernel."""
 
@@ -128,9 +138,25 @@ class SetCriterion(nn.Module):
     def loss_boxes(self, outputs, targets, indices, num_boxes, box_type):
         assert 'pred_boxes' in outputs
         pred = outputs['pred_boxes']
-        batch_idx, src_idx = self._get_src_permutation_idx(indices)
-        src_row = (batch_idx * pred.shape[1] + src_idx).to(pred.device)
-        target_boxes = torch.cat([t['boxes'][i.to(t['boxes'].device)] for t, (_, i) in zip(targets, indices)], dim=0)
+        all_boxes = _packed(targets, "boxes")
+        last = getattr(self.matcher, "_last", None)
+        if last is not None and last[0] is indices:
+            # indices straight from our matcher: pair lists are still on the device; only two small host index arrays
+            # (image id and slot of every matched pair, known from the per-image counts) are uploaded
+            _, ri, ci, counts, starts, nq = last
+            bidx = np.repeat(np.arange(len(counts)), counts)
+            kidx = np.arange(len(bidx)) - np.repeat(np.cumsum(counts) - counts, counts)
+            sel = torch.from_numpy(np.stack([bidx, kidx, starts[bidx]])).to(pred.device, non_blocking=True)
+            src_row = sel[0] * nq + ri[sel[0], sel[1]]
+            target_boxes = all_boxes[sel[2] + ci[sel[0], sel[1]]]
+        else:
+            batch_idx, src_idx = self._get_src_permutation_idx(indices)
+            src_row = (batch_idx * pred.shape[1] + src_idx).to(pred.device)
+            starts_, flat = 0, []
+            for t, (_, i) in zip(targets, indices):        # one gather over the packed targets (:164)
+                flat.append(i + starts_)
+                starts_ += len(t['boxes'])
+            target_boxes = all_boxes[torch.cat(flat).to(all_boxes.device)]
         pred_flat = pred.flatten(0, 1)
         if pred_flat.dtype != torch.float32 or not pred_flat.is_contiguous():
             pred_flat = pred_flat.float().contiguous()
@@ -157,10 +183,11 @@ class SetCriterion(nn.Module):
         outputs_without_aux = {k: v for k, v in outputs.items() if k != 'aux_outputs'}
         indices_last = self.matcher(outputs_without_aux, targets, exclude_class=exclude_class)
         num_boxes = sum(len(t["labels"]) for t in targets)
-        num_boxes = torch.as_tensor([num_boxes], dtype=torch.float, device=next(iter(outputs.values())).device)
         if is_dist_avail_and_initialized():
-            torch.distributed.all_reduce(num_boxes)
-        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=next(iter(outputs.values())).device)
+            torch.distributed.all_reduce(nb)
+            num_boxes = nb.item()
+        num_boxes = max(float(num_boxes) / get_world_size(), 1.0)
         losses = {}
         for loss in self.losses:
             losses.update(self.get_loss(loss, outputs, targets, indices_last, num_boxes, box_type))
@@ -178,7 +205,7 @@ def prepare_targets(boxes, classes, image_size, center_crop=True):
     """Reference :249-279: xyxy pixel boxes -> per-image dicts of normalised cxcywh boxes (absent / degenerate boxes
     dropped).  Unlike the reference (:255 `.cuda()`), tensors stay on the device of `boxes`."""
     if classes is None:
-        classes = torch.stack([1 - (box.sum(-1) != 0).float() for box in boxes]).to(boxes.device)
+        classes = 1 - (boxes.sum(-1) != 0).float()            # dummy labels, as the reference builds them (:254)
     if center_crop:
         shift = torch.zeros_like(boxes)
         dis = (image_size[:, 1] - image_size[:, 0]) / 2
@@ -191,11 +218,14 @@ def prepare_targets(boxes, classes, image_size, center_crop=True):
         boxes = torch.clip(boxes, min=0, max=256).div(256)
     else:
         boxes = torch.clip(boxes, min=0, max=224).div(224)
-    out = []
-    for c_, b_ in zip(classes, boxes):
-        avail = (c_ != -1) * (b_[:, 2] > b_[:, 0]) * (b_[:, 3] > b_[:, 1])
-        kept = b_[avail, :]
-        out.append({'labels': c_[avail], 'boxes': box_ops.box_xyxy_to_cxcywh(kept)})
+    # all images at once (the reference loops over images with one boolean index each, :270-278): one mask, one box
+    # conversion, one host read of the per-image counts; the per-image dicts are views into the packed tensors
+    avail = (classes != -1) & (boxes[..., 2] > boxes[..., 0]) & (boxes[..., 3] > boxes[..., 1])
+    counts = avail.sum(1).tolist()
+    packed_boxes = box_ops.box_xyxy_to_cxcywh(boxes[avail])
+    packed_labels = classes[avail]
+    out = _PackedTargets({'labels': l, 'boxes': b} for l, b in zip(packed_labels.split(counts), packed_boxes.split(counts)))
+    out.boxes, out.labels, out.counts = packed_boxes, packed_labels, counts
     return out
 
 
