@@ -83,11 +83,15 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float bsum = 0.f;  // threads 0..31 of the k-tile-0 CTAs own one bias entry
-  for (int r0 = 0; r0 < a.R; r0 += 32) {
+  // split-R: CTA z reduces rows [z * rows_per_split, ...) and adds its partial tile atomically (outputs pre-zeroed or
+  // accumulating, see the host wrapper)
+  const int r_begin = blockIdx.z * a.rows_per_split;
+  const int r_end = (r_begin + a.rows_per_split < a.R) ? r_begin + a.rows_per_split : a.R;
+  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
     for (int idx = tid; idx < 32 * 32; idx += 256) {
       const int r = idx >> 5, n = idx & 31;
       float v = 0.f;
-      if (r0 + r < a.R && n0 + n < a.N) {
+      if (r0 + r < r_end && n0 + n < a.N) {
         v = a.dY[static_cast<size_t>(r0 + r) * a.ldy + n0 + n];
         if (a.act) v = act_grad(v, a.Y[static_cast<size_t>(r0 + r) * a.ldyo + n0 + n], a.act);
       }
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
     for (int idx = tid; idx < 32 * 64; idx += 256) {
       const int r = idx >> 6, k = idx & 63;
       float v = 0.f;
-      if (r0 + r < a.R && k0 + k < a.K) {
+      if (r0 + r < r_end && k0 + k < a.K) {
         v = a.X[static_cast<size_t>(r0 + r) * a.ldx + k0 + k];
         if (a.x_add) v += a.x_add[static_cast<size_t>((r0 + r) % a.add_mod) * a.K + k0 + k];
         if (a.in_relu) v = fmaxf(v, 0.f);
@@ -127,12 +131,14 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
       const int k = k0 + tx + 16 * j;
       if (k >= a.K) continue;
       float* d = a.dW + static_cast<size_t>(n) * a.ldw + k;
-      *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * acc[i][j];
+      if (gridDim.z > 1) atomicAdd(d, a.scale * acc[i][j]);
+      else *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * acc[i][j];
     }
   }
   if (a.db && blockIdx.x == 0 && tid < 32 && n0 + tid < a.N) {
     float* d = a.db + n0 + tid;
-    *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * bsum;
+    if (gridDim.z > 1) atomicAdd(d, a.scale * bsum);
+    else *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * bsum;
   }
 }
 
@@ -507,10 +513,25 @@ int linear_dgrad_f32(const LinBwdArgs& a, cudaStream_t s) {
   return 0;
 }
 
-int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s) {
+int linear_wgrad_f32(const LinBwdArgs& a_in, cudaStream_t s) {
+  LinBwdArgs a = a_in;
   HH_REQUIRE(a.R > 0 && a.N > 0 && a.K > 0 && a.dY && a.X && a.dW, "linear_wgrad: bad argument");
   HH_REQUIRE(a.act == 0 || a.Y != nullptr, "linear_wgrad: activation derivative needs the saved output");
   dim3 grid((a.K + 63) / 64, (a.N + 31) / 32);
+  // Few output tiles but many rows: split the row reduction over gridDim.z so that ~4 CTAs per SM are in flight; the
+  // partial tiles are combined with fp32 atomics (summation order, hence the last bits, vary from run to run).
+  int split = (4 * num_sms() + static_cast<int>(grid.x * grid.y) - 1) / static_cast<int>(grid.x * grid.y);
+  const int max_split = (a.R + 127) / 128;  // at least 128 rows per CTA
+  if (split > max_split) split = max_split;
+  if (split > 64) split = 64;
+  if (split < 1 || (a.beta != 0.f && a.beta != 1.f)) split = 1;
+  a.rows_per_split = ((a.R + split - 1) / split + 31) / 32 * 32;
+  split = (a.R + a.rows_per_split - 1) / a.rows_per_split;
+  grid.z = split;
+  if (split > 1 && a.beta == 0.f) {
+    HH_CHECK_CUDA(cudaMemset2DAsync(a.dW, static_cast<size_t>(a.ldw) * 4, 0, static_cast<size_t>(a.K) * 4, a.N, s));
+    if (a.db) HH_CHECK_CUDA(cudaMemsetAsync(a.db, 0, static_cast<size_t>(a.N) * 4, s));
+  }
   linear_wgrad_kernel<<<grid, 256, 0, s>>>(a);
   HH_CHECK_LAUNCH("linear_wgrad_kernel");
   return 0;

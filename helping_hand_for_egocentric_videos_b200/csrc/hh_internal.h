@@ -151,6 +151,7 @@ struct LinBwdArgs {
   float* db;
   int R, N, K;
   float beta, scale;
+  int rows_per_split;   // set by linear_wgrad_f32
 };
 int linear_dgrad_f32(const LinBwdArgs& a, cudaStream_t s);
 int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s);
