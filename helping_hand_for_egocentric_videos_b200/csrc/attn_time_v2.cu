@@ -3,6 +3,11 @@
 //     query slots that are constant (CLS row) or always zero are single shared rows addressed per lane by ldmatrix,
 //     so a warp needs 12.5 KB and its loads can be DOUBLE-BUFFERED: the 3*T row segments of patch position p+1 are in
 //     flight (cp.async) while position p is computed -> twice the bytes in flight per SM for this HBM-bound kernel.
+//   * the frame count is a template parameter for T = 4 / 8 / 16 (every configuration the reference runs): the copy
+//     loops are fully unrolled over per-lane base pointers + warp-uniform offsets, so a 16-byte cp.async costs ~2
+//     instructions instead of the ~60 of the runtime-T index arithmetic (integer division by T, swizzle, 64-bit
+//     address) that made the first version issue-bound at 46 % of HBM bandwidth. TT = 0 keeps the runtime-T loops.
+#include <cstdlib>
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
 
@@ -25,9 +30,11 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+template <int TT>
 __global__ void __launch_bounds__(TW * 32, 2)
-attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ cls_part, int T, int n,
+attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ cls_part, int Trt, int n,
                     int H, int pchunk, int nchunks) {
+  const int T = TT ? TT : Trt;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t base = smem_u32(smem_raw) + static_cast<uint32_t>(warp * WARP_BYTES);
@@ -80,13 +87,34 @@ attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
   const int p_begin = chunk * pchunk;
   const int p_end = min(n, p_begin + pchunk);
 
+  // fast path (TT % 4 == 0): lane -> (frame row lrow + 4i, 16-byte chunk lch); row & 7 = lrow + 4 * (i & 1)
+  const int lrow = lane >> 3, lch = lane & 7;
+  const bf16* ld_lane = clip + (1 + static_cast<size_t>(lrow) * n) * ld + lch * 8;
+  const size_t ld_step4 = static_cast<size_t>(4) * n * ld;          // four frames further
+  const uint32_t sm_lane0 = base + lrow * 128 + ((lch ^ lrow) << 4);        // rows lrow + 8j
+  const uint32_t sm_lane1 = base + (lrow + 4) * 128 + ((lch ^ (lrow + 4)) << 4);  // rows lrow + 4 + 8j
+  bf16* st_lane = out + (static_cast<size_t>(b) * N + 1 + static_cast<size_t>(lrow) * n) * D + h * HD + lch * 8;
+  const size_t st_step4 = static_cast<size_t>(4) * n * D;
+
   auto issue_loads = [&](int buf, int p) {
-    for (int c = lane; c < 3 * T * 8; c += 32) {
-      const int ch = c & 7;
-      const int r = c >> 3;
-      const int which = r / T, f = r - which * T;
-      const bf16* src = clip + (1 + static_cast<size_t>(f) * n + p) * ld + which * D + ch * 8;
-      cp16(sw_addr(base, buf * BUF_ROWS + which * 16 + f, ch), src);
+    if constexpr (TT != 0) {
+      const bf16* src = ld_lane + static_cast<size_t>(p) * ld;
+      const uint32_t boff = buf * (BUF_ROWS * 128);
+#pragma unroll
+      for (int i = 0; i < 3 * TT / 4; ++i) {
+        const int which = (4 * i) / TT, f4 = ((4 * i) % TT) / 4;   // compile-time after unrolling
+        const int row = which * 16 + 4 * f4;                       // + lrow, folded into sm_lane*
+        const uint32_t dst = ((f4 & 1) ? sm_lane1 + (row - 4) * 128 : sm_lane0 + row * 128) + boff;
+        cp16(dst, src + f4 * ld_step4 + which * D);
+      }
+    } else {
+      for (int c = lane; c < 3 * T * 8; c += 32) {
+        const int ch = c & 7;
+        const int r = c >> 3;
+        const int which = r / T, f = r - which * T;
+        const bf16* src = clip + (1 + static_cast<size_t>(f) * n + p) * ld + which * D + ch * 8;
+        cp16(sw_addr(base, buf * BUF_ROWS + which * 16 + f, ch), src);
+      }
     }
     cp_async_commit();
   };
@@ -216,14 +244,28 @@ attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(pack_bf16x2(o[ni][2] * i1, o[ni][3] * i1)) : "memory");
     }
     __syncwarp();
-    for (int c = lane; c < T * 8; c += 32) {
-      const int f = c >> 3, ch = c & 7;
-      uint4 v;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                   : "r"(sw_addr(base, qb + f, ch)));
-      bf16* dst = out + (static_cast<size_t>(b) * N + 1 + static_cast<size_t>(f) * n + p) * D + h * HD + ch * 8;
-      *reinterpret_cast<uint4*>(dst) = v;
+    if constexpr (TT != 0) {
+      bf16* dstp = st_lane + static_cast<size_t>(p) * D;
+      const uint32_t boff = buf * (BUF_ROWS * 128);
+#pragma unroll
+      for (int j = 0; j < TT / 4; ++j) {
+        uint4 v;
+        const uint32_t src = ((j & 1) ? sm_lane1 + (4 * j - 4) * 128 : sm_lane0 + 4 * j * 128) + boff;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(src));
+        *reinterpret_cast<uint4*>(dstp + j * st_step4) = v;
+      }
+    } else {
+      for (int c = lane; c < T * 8; c += 32) {
+        const int f = c >> 3, ch = c & 7;
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(sw_addr(base, qb + f, ch)));
+        bf16* dst = out + (static_cast<size_t>(b) * N + 1 + static_cast<size_t>(f) * n + p) * D + h * HD + ch * 8;
+        *reinterpret_cast<uint4*>(dst) = v;
+      }
     }
     __syncwarp();  // this buffer is refilled by the prefetch issued at the top of the next iteration
   }
@@ -246,20 +288,33 @@ attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
 
 }  // namespace
 
-int attn_time_v2(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, int pchunk, int nchunks,
-                 cudaStream_t stream) {
+template <int TT>
+static int launch_v2(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, int pchunk, int nchunks,
+                     cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(TW) * WARP_BYTES;
   static bool configured = false;
   if (!configured) {
-    HH_CHECK_CUDA(cudaFuncSetAttribute(attn_time_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HH_CHECK_CUDA(cudaFuncSetAttribute(attn_time_v2_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     configured = true;
   }
   const long long blocks = static_cast<long long>(B) * ((H + TW - 1) / TW) * nchunks;
   HH_REQUIRE(blocks < (1ll << 31), "attn_time: grid too large");
-  attn_time_v2_kernel<<<static_cast<unsigned>(blocks), TW * 32, smem, stream>>>(qkv, out, cls_ws, T, n, H, pchunk, nchunks);
+  attn_time_v2_kernel<TT><<<static_cast<unsigned>(blocks), TW * 32, smem, stream>>>(qkv, out, cls_ws, T, n, H, pchunk,
+                                                                                     nchunks);
   HH_CHECK_LAUNCH("attn_time_v2_kernel");
   return 0;
+}
+
+int attn_time_v2(const bf16* qkv, bf16* out, int B, int T, int n, int H, float* cls_ws, int pchunk, int nchunks,
+                 cudaStream_t stream) {
+  static const bool generic = std::getenv("HH_ATTN_TIME_GENERIC") != nullptr;  // differential testing of the TT paths
+  if (!generic) {
+    if (T == 16) return launch_v2<16>(qkv, out, B, T, n, H, cls_ws, pchunk, nchunks, stream);
+    if (T == 8) return launch_v2<8>(qkv, out, B, T, n, H, cls_ws, pchunk, nchunks, stream);
+    if (T == 4) return launch_v2<4>(qkv, out, B, T, n, H, cls_ws, pchunk, nchunks, stream);
+  }
+  return launch_v2<0>(qkv, out, B, T, n, H, cls_ws, pchunk, nchunks, stream);
 }
 
 }  // namespace hh
