@@ -30,12 +30,12 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int STAGE_LD = 33;  // per-warp transpose buffer: 32 rows x 33 words
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWOSM = false>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256 && !TWOSM) ? 4 : 6;
   static constexpr int EPI_SLOTS = 2;                              // per-warp ring of 32-row x 128-byte store slots
   static constexpr int EPI_BYTES = 4 * EPI_SLOTS * 4096;            // (>= the 4 x 32 x 33 words of the direct path)
   static constexpr int BIAS_BYTES = BLOCK_N * 4;
@@ -72,11 +72,19 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // weight tile: each CTA fetches half of the W tile and multicasts it into both CTAs' shared memory, which cuts the
 // L2 -> SM operand traffic per tile from A + W to A + W/2 (-33 %).  A stage is released to the producers only after
 // BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto both empty barriers).
-template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER>
+// TWOSM (implies CLUSTER): the pair runs ONE tcgen05.mma.cta_group::2 of 256 x BLOCK_N x 16 per step instead of two
+// independent 128 x BLOCK_N MMAs.  Each CTA stages its own 128 rows of A and only ITS half of the W tile (no multicast);
+// the leader CTA's single MMA thread drives both SMs' tensor cores, which read the W halves from both shared memories.
+// Shared-memory operand reads per CTA drop from 128 + BLOCK_N to 128 + BLOCK_N/2 rows per K step (-33 %), a stage is
+// 32 KB instead of 48 KB (6 stages instead of 4).  Barrier protocol: both producers' TMA loads complete on the LEADER's
+// full barrier (which expects both CTAs' bytes); the leader's commits are multicast to both CTAs' empty / accumulator-
+// full barriers; both CTAs' epilogue warps arrive on the LEADER's accumulator-empty barrier.
+template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER, bool TWOSM = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const GemmArgs p) {
-  using C = Cfg<BLOCK_N>;
+  static_assert(!TWOSM || (CLUSTER && TMA_STORE), "the 2-SM MMA path runs as a CTA pair");
+  using C = Cfg<BLOCK_N, TWOSM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -107,17 +115,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CLUSTER ? 2 : 1);
+      mbar_init(&empty_bar[s], (CLUSTER && !TWOSM) ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], TWOSM ? 8 : 4);   // 2-SM: the leader's barrier collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (TWOSM) {
+      tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -138,6 +151,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
+          if constexpr (TWOSM) {  // my A rows + my half of the W tile, into MY smem, signalled on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_2sm(&tma_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d_2sm(&tma_b, &full_bar[stage], sb, kb * BLOCK_K, n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
           if constexpr (CLUSTER) {  // my half of the W tile, into both CTAs (box = BLOCK_N/2 rows)
@@ -155,8 +178,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && (!TWOSM || cta_rank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TWOSM ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -175,18 +198,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance K inside the 128-byte swizzle row: +32 bytes => +2 in (addr >> 4) units
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            if constexpr (TWOSM)
+              umma_bf16_2sm(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
           }
           // smem slot reusable once these MMAs retire (in a pair: tell both CTAs' producers)
-          if constexpr (CLUSTER) umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>(3));
+          if constexpr (TWOSM) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>(3));
+          else if constexpr (CLUSTER) umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>(3));
           else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if constexpr (TWOSM) umma_commit_2sm(&tfull_bar[acc], static_cast<uint16_t>(3));  // both CTAs' epilogues
+        else umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -337,7 +366,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above) -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (TWOSM) mbar_arrive_cluster(&tempty_bar[acc], 0u);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -355,7 +387,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if constexpr (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (TWOSM) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -392,11 +425,11 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
   return 0;
 }
 
-template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER>
+template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER, bool TWOSM = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& args, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, TWOSM>;
   static bool configured = false;
-  auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE, CLUSTER>;
+  auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE, CLUSTER, TWOSM>;
   if (!configured) {
     HH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
@@ -430,7 +463,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 
 template <int BLOCK_N>
 int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, bool tma_store, bool cluster,
-                 const GemmArgs& args, int epi, cudaStream_t stream) {
+                 bool twosm, const GemmArgs& args, int epi, cudaStream_t stream) {
+  if constexpr (BLOCK_N == 256) {
+    if (tma_store && cluster && twosm) {
+      switch (epi) {
+        case EPI_BIAS_BF16: return launch<256, EPI_BIAS_BF16, true, true, true>(ta, tb, tc, args, stream);
+        case EPI_BIAS_QGELU_BF16: return launch<256, EPI_BIAS_QGELU_BF16, true, true, true>(ta, tb, tc, args, stream);
+        case EPI_BIAS_F32: return launch<256, EPI_BIAS_F32, true, true, true>(ta, tb, tc, args, stream);
+      }
+    }
+  }
   if (tma_store && cluster) {
     switch (epi) {
       case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, true>(ta, tb, tc, args, stream);
@@ -481,6 +523,9 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   // CTA pairs sharing the W tile (multicast) once there are enough row tiles to pair up
   static const bool cluster_ok = std::getenv("HH_GEMM_NO_CLUSTER") == nullptr;
   const bool cluster = cluster_ok && tma_store && tiles_m >= num_sms() / 2 && (num_sms() % 2 == 0);
+  // CTA pairs on one 256-row MMA (cta_group::2) for the wide tiles; HH_GEMM_1SM=1 keeps the multicast 1-SM pairs
+  static const bool twosm_ok = std::getenv("HH_GEMM_1SM") == nullptr;
+  const bool twosm = cluster && twosm_ok && bn == 256;
   CUtensorMap ta, tb, tc;
   int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
   if (rc) return rc;
@@ -504,8 +549,8 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   args.ldr = ldr;
   args.tiles_m = tiles_m;
   args.tiles_n = (N + bn - 1) / bn;
-  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, cluster, args, epilogue, stream);
-  return dispatch_epi<128>(ta, tb, tc, tma_store, cluster, args, epilogue, stream);
+  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, cluster, twosm, args, epilogue, stream);
+  return dispatch_epi<128>(ta, tb, tc, tma_store, cluster, false, args, epilogue, stream);
 }
 
 }  // namespace hh
