@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhh_b200.so")
+# HH_B200_LIB: developer override to A/B two builds of the same library on one GPU box (never a different backend)
+LIB_PATH = os.environ.get("HH_B200_LIB") or os.path.join(_HERE, "libhh_b200.so")
 
 
 class EncoderCfg(C.Structure):

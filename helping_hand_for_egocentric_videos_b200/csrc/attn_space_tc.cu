@@ -368,6 +368,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     const int nvalid = min(128, max(0, p.n - key_base));    // valid keys in this thread's column group
     const int nch = (nvalid + 31) >> 5;
     int u = 0;
+    int release_st = -1;   // stage whose output store may still be reading its staging rows: released one task later,
+                           // after the next task's first pass, instead of stalling the epilogue on the bulk-store read
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++u) {
       const int st = u & 1;
       const uint32_t ph = (u >> 1) & 1;
@@ -404,6 +406,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
       mx = fmaxf(mx, ex->xm[hf][cg ^ 1][rl]);
       if (tr) trace_ev(p, 3 + jh, u, 1);
+      if (release_st >= 0 && lane == 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&ex->empty[release_st]);
+      }
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
 
@@ -491,13 +497,13 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           tma_store_4d(&tm_out, stg, h * HD + cg * 32, row0, f, b);
           tma_store_commit();
         }
-        tma_store_wait_read<0>();   // the store has read its staging rows: this warp is done with the stage
-        mbar_arrive(&ex->empty[st]);
       }
+      release_st = st;
       __syncwarp();
       if (tr) trace_ev(p, 3 + jh, u, 4);
      }
     }
+    if (lane == 0) tma_store_wait_read<0>();   // shared memory stays valid until the last store has read it
   }
 
   tc_fence_before();

@@ -230,6 +230,7 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
   RC(ws_tok.reserve(Pc * D * 4));
   RC(ws_x.reserve(Mc * D * 4));
   RC(ws_dl.reserve(Mc * D * 2));
+  RC(ws_dl2.reserve(Mc * D * 2));
   RC(ws_a.reserve(Mc * D * 2));
   RC(ws_qkv.reserve(Mc * 3 * D * 2));
   RC(ws_h.reserve(Mc * Hd * 2));
@@ -238,6 +239,7 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
   float* tok = static_cast<float*>(ws_tok.ptr);
   float* x = static_cast<float*>(ws_x.ptr);
   bf16* dl = static_cast<bf16*>(ws_dl.ptr);
+  bf16* dls = static_cast<bf16*>(ws_dl2.ptr);   // spatial branch output, pending until the next layer's norm3
   bf16* a = static_cast<bf16*>(ws_a.ptr);
   bf16* qkv = static_cast<bf16*>(ws_qkv.ptr);
   bf16* h = static_cast<bf16*>(ws_h.ptr);
@@ -261,12 +263,18 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
     PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
                                      weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
     launches += 3;
-    const bf16* pending = nullptr;  // bf16 branch output not yet folded into the fp32 residual stream x
-    auto ln_fused = [&](const bf16* delta, bool write_x, const std::string& nm, float eps, bf16* out16, float* out32) {
+    // bf16 branch outputs not yet folded into the fp32 residual stream x: the spatial-attention output and the MLP
+    // output of a layer are BOTH added by the next layer's norm3 pass, x <- (x + space_out) + mlp_out -- the same two
+    // fp32 additions in the same order as adding them one at a time, but x is written once per layer instead of twice
+    const bf16* pending = nullptr;
+    const bf16* pending2 = nullptr;
+    auto ln_fused = [&](const bf16* delta, const bf16* delta2, bool write_x, const std::string& nm, float eps,
+                        bf16* out16, float* out32) {
       LnArgs ln{};
       ln.x = x;
       ln.ldx = D;
       ln.delta = delta;
+      ln.delta2 = delta2;
       ln.xsum_out = (delta && write_x) ? x : nullptr;
       ln.w = weights.get(nm + ".weight");
       ln.b = weights.get(nm + ".bias");
@@ -283,30 +291,32 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
     for (int i = 0; i < nblocks; ++i) {
       const std::string p = "blocks." + std::to_string(i) + ".";
       const Layer& L = layers[i];
-      // Residual adds are folded into the LayerNorm that follows them (one fp32 pass instead of a GEMM-epilogue
-      // read-modify-write):  norm3 reads x + mlp_out(prev) and stores it as the new x;  norm1 reads x + time_out
-      // (never stored: 'frozen-in-time' discards it, LaviLa.py:364,384);  norm2 reads x + space_out and stores it.
+      // Residual adds are folded into the LayerNorms (fp32 passes instead of GEMM-epilogue read-modify-writes):
+      //   norm3 reads x + space_out(prev) + mlp_out(prev) and stores it as the new x;
+      //   norm1 reads x + time_out (never stored: 'frozen-in-time' discards it, LaviLa.py:364,384);
+      //   norm2 reads x + space_out (not stored either: the sum is formed again, bit-identically, by the next norm3).
       for (int at = 0; at < 2; ++at) {  // 0 = time (norm3), 1 = space (norm1)
         const std::string q = p + (at == 0 ? "timeattn" : "attn");
-        if (at == 0) RC(ln_fused(pending, true, p + "norm3", 1e-6f, a, nullptr));
-        else RC(ln_fused(dl, false, p + "norm1", 1e-6f, a, nullptr));
+        if (at == 0) RC(ln_fused(pending, pending2, true, p + "norm3", 1e-6f, a, nullptr));
+        else RC(ln_fused(dl, nullptr, false, p + "norm1", 1e-6f, a, nullptr));
         PROF(K_GEMM_QKV, gemm_bf16(a, D, static_cast<const bf16*>(L.w_qkv[at].ptr), D, qkv, 3 * D,
                                    static_cast<const float*>(L.b_qkv[at].ptr), nullptr, 0, M, 3 * D, D, EPI_BIAS_BF16, s));
         if (at == 0) PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, cls_ws, s));
         else PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, cls_ws, s));
-        PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, dl, D,
+        PROF(K_GEMM_PROJ, gemm_bf16(a, D, static_cast<const bf16*>(L.w_proj[at].ptr), D, at == 0 ? dl : dls, D,
                                     weights.get(q + ".proj.bias"), nullptr, 0, M, D, D, EPI_BIAS_BF16, s));
         launches += 5;
       }
-      RC(ln_fused(dl, true, p + "norm2", 1e-6f, a, nullptr));  // x <- x + space_out ; a = norm2(x)
+      RC(ln_fused(dls, nullptr, false, p + "norm2", 1e-6f, a, nullptr));  // a = norm2(x + space_out)
       PROF(K_GEMM_FC1, gemm_bf16(a, D, static_cast<const bf16*>(L.w_fc1.ptr), D, h, Hd, weights.get(p + "mlp.fc1.bias"), nullptr,
                                  0, M, Hd, D, EPI_BIAS_QGELU_BF16, s));
       PROF(K_GEMM_FC2, gemm_bf16(h, Hd, static_cast<const bf16*>(L.w_fc2.ptr), Hd, dl, D, weights.get(p + "mlp.fc2.bias"), nullptr,
                                  0, M, D, Hd, EPI_BIAS_BF16, s));
-      pending = dl;  // x + mlp_out is formed by the next norm3 (or the final norm)
+      pending = dls;   // x + space_out + mlp_out is formed by the next norm3 (or the final norm)
+      pending2 = dl;
       launches += 3;
     }
-    RC(ln_fused(pending, false, "norm", 1e-6f, nullptr, fmap + static_cast<size_t>(b0) * N * D));
+    RC(ln_fused(pending, pending2, false, "norm", 1e-6f, nullptr, fmap + static_cast<size_t>(b0) * N * D));
     launches += 1;
   }
   return 0;

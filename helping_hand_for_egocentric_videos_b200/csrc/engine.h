@@ -63,7 +63,7 @@ struct Encoder {
   };
   std::vector<Layer> layers;
   DevBuf w_patch;
-  DevBuf ws_patches, ws_tok, ws_x, ws_dl, ws_a, ws_qkv, ws_h, ws_cls;
+  DevBuf ws_patches, ws_tok, ws_x, ws_dl, ws_dl2, ws_a, ws_qkv, ws_h, ws_cls;
 
   explicit Encoder(const hh_encoder_cfg& c);
   static int validate(const hh_encoder_cfg& c);

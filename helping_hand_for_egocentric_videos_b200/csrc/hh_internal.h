@@ -53,6 +53,7 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
 struct LnArgs {
   const float* x; int ldx;
   const bf16* delta;    // optional bf16 [M, D]: the norm is taken of x + delta (fused residual add)
+  const bf16* delta2;   // optional second bf16 [M, D] (only with delta): (x + delta) + delta2
   float* xsum_out;      // optional fp32 [M, D]: receives x + delta (may alias x)
   const float* w; const float* b; float eps;
   float* out_f32; bf16* out_bf16;

@@ -36,6 +36,19 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
         v[j].x += d0.x; v[j].y += d0.y; v[j].z += d1.x; v[j].w += d1.y;
       }
     }
+    if (a.delta2) {  // second pending branch output, added after the first: (x + delta) + delta2
+      const bf16* dr2 = a.delta2 + static_cast<size_t>(warp) * a.D;
+#pragma unroll
+      for (int j = 0; j < LN_MAX_VEC; ++j)
+        if (j < nv) dv[j] = __ldcs(reinterpret_cast<const uint2*>(dr2 + (j * 32 + lane) * 4));
+#pragma unroll
+      for (int j = 0; j < LN_MAX_VEC; ++j) {
+        if (j < nv) {
+          const float2 d0 = unpack_bf16x2(dv[j].x), d1 = unpack_bf16x2(dv[j].y);
+          v[j].x += d0.x; v[j].y += d0.y; v[j].z += d1.x; v[j].w += d1.y;
+        }
+      }
+    }
     if (a.xsum_out) {
       float* xo = a.xsum_out + static_cast<size_t>(warp) * a.D;
 #pragma unroll
