@@ -6,6 +6,7 @@
 // The CLS *query* (which attends all 1+T*n keys, LaviLa.py:258) rides along as one extra 16-row block per CTA whose
 // only live row is q_cls: its (max, sum, o[64]) over this frame's keys is written as a partial per (clip, head, frame)
 // and folded, with the CLS key itself, into output row 0 by attn_cls_merge (attn_time.cu).
+#include <cstdlib>
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
 

@@ -89,12 +89,13 @@ def gemm_full():
     out += ["## Reading", "",
             "* The mainloop keeps the tensor pipe 80-90 % active; K=1024 tiles lose a little to the epilogue "
             "(TMEM -> registers -> swizzled smem -> bulk tensor store), K=4096 tiles (fc2) the least.",
-            "* DRAM traffic is at or below the algorithmic bytes (A streamed once, W L2-resident; CTA pairs share each W "
-            "tile through TMA multicast): no wasted re-reads.",
-            "* 148 CTAs (74 clusters of 2) x 256 threads, 1 CTA/SM, 231.7 KB dynamic smem (4 x 48 KB TMA stages + 32 KB "
-            "store ring), 512 TMEM columns (2 accumulators).",
-            "* SASS: `UTCHMMA` (tcgen05.mma), `UTMALDG.2D[.MULTICAST]`, `UTMASTG.2D`, `LDTM`, `UTCBAR` present "
-            "(`cuobjdump -sass libhh_b200.so`)."]
+            "* DRAM traffic is at or below the algorithmic bytes (A streamed once, W L2-resident; each CTA of a pair "
+            "fetches only its half of the W tile): no wasted re-reads.",
+            "* 148 CTAs (74 clusters of 2) x 256 threads, 1 CTA/SM; each pair runs ONE `tcgen05.mma.cta_group::2` "
+            "(256 x 256 x 16) per K step: 231.7 KB dynamic smem (6 x 32 KB TMA stages + 32 KB store ring), 512 TMEM "
+            "columns per CTA (2 accumulators of its 128 rows).",
+            "* SASS: `UTCHMMA.2CTA` (tcgen05.mma.cta_group::2), `UTMALDG.2D.2CTA`, `UTMASTG.2D`, `LDTM`, "
+            "`UTCBAR.2CTA.MULTICAST` present (`cuobjdump -sass libhh_b200.so`)."]
     open("profiles/%s_gemm_ncu_full.md" % R, "w").write("\n".join(out) + "\n")
     json.dump({"source": "ncu --set full, tools/prof_kernels.py gemm 64 1 (M=262208)", "kernels": traffic},
               open("profiles/%s_gemm_traffic.json" % R, "w"), indent=1)
