@@ -48,6 +48,7 @@ SIGNATURES = {
     "hh_decoder_set_weight": (_i, [_p, C.c_char_p, _p, _i64, _p]),
     "hh_decoder_forward": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
     "hh_decoder_forward_train": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
+    "hh_decoder_set_dropout": (_i, [_p, _f, C.c_uint64, C.c_uint32]),
     "hh_decoder_backward": (_i, [_p, _p, _p, _p, _p, _p]),
     "hh_decoder_get_grad": (_i, [_p, C.c_char_p, _p, _i64, _p]),
     "hh_decoder_flops_per_clip": (C.c_double, [_p, _i]),

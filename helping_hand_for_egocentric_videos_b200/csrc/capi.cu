@@ -106,6 +106,23 @@ int hh_decoder_forward_train(hh_decoder* dec, const float* features, int64_t str
   return dec->impl.forward(features, stride_b, stride_row, B, T, hs, logits, boxes, S(stream), true);
   HH_GUARD_END
 }
+int hh_decoder_set_dropout(hh_decoder* dec, float p, uint64_t seed, uint32_t offset) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_set_dropout: null handle");
+  if (!(p >= 0.f && p < 1.f)) return fail(-2, "hh_decoder_set_dropout: p must be in [0, 1)");
+  DropCfg d = drop_off();
+  if (p > 0.f) {
+    d.thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);   // keep <=> 16-bit lane >= thr
+    if (d.thr == 0) d.thr = 1;
+    d.scale = 1.0f / (1.0f - p);
+    d.seed_lo = static_cast<uint32_t>(seed);
+    d.seed_hi = static_cast<uint32_t>(seed >> 32);
+    d.offset = offset;
+  }
+  dec->impl.next_drop = d;
+  return 0;
+  HH_GUARD_END
+}
 int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, const float* d_hs, const float* d_boxes,
                         void* stream) {
   HH_GUARD_BEGIN

@@ -24,7 +24,8 @@ constexpr int XBLK = 64;        // keys per block
 
 __global__ void __launch_bounds__(XW * 32, 3)
 cross_attn_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
-                      float* __restrict__ part, int Q, int heads, int S, int splits, int keys_per_warp) {
+                      float* __restrict__ part, int Q, int heads, int S, int splits, int keys_per_warp, DropCfg drop,
+                      uint32_t drop_site) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bf16* Ks = reinterpret_cast<bf16*>(smem_raw) + static_cast<size_t>(warp) * (2 * XBLK * XLD);
@@ -124,8 +125,26 @@ cross_attn_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, c
       const float p2 = fast_exp2(fmaf(s[ni][2], LOG2E, -ml1)), p3 = fast_exp2(fmaf(s[ni][3], LOG2E, -ml1));
       l0 += p0 + p1;
       l1 += p2 + p3;
-      pa[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      float d0 = p0, d1 = p1, d2 = p2, d3 = p3;
+      if (drop.thr) {  // training: probabilities are dropped AFTER normalisation -> l keeps every key, P V only the kept
+        // keys 8*ni .. 8*ni+7 of a row are one Philox block (S % 8 == 0); this thread owns lanes 2t, 2t+1 of two rows
+        const int key = kb + ni * 8;
+        uint32_t rb[4];
+        if (g < Q) {
+          drop_block8(drop, drop_site, ((static_cast<uint64_t>(b) * heads + h) * Q + g) * (S >> 3) + (key >> 3), rb);
+          const uint32_t w = t == 0 ? rb[0] : t == 1 ? rb[1] : t == 2 ? rb[2] : rb[3];
+          if ((w & 0xFFFFu) < drop.thr) d0 = 0.f;
+          if ((w >> 16) < drop.thr) d1 = 0.f;
+        }
+        if (g + 8 < Q) {
+          drop_block8(drop, drop_site, ((static_cast<uint64_t>(b) * heads + h) * Q + g + 8) * (S >> 3) + (key >> 3), rb);
+          const uint32_t w = t == 0 ? rb[0] : t == 1 ? rb[1] : t == 2 ? rb[2] : rb[3];
+          if ((w & 0xFFFFu) < drop.thr) d2 = 0.f;
+          if ((w >> 16) < drop.thr) d3 = 0.f;
+        }
+      }
+      pa[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16x2(d0, d1);
+      pa[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16x2(d2, d3);
       o[ni][0] *= c0; o[ni][1] *= c0; o[ni][2] *= c1; o[ni][3] *= c1;
     }
 #pragma unroll
@@ -166,7 +185,7 @@ cross_attn_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, c
 }
 
 __global__ void __launch_bounds__(HD)
-cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int Q, int heads, int nparts) {
+cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int Q, int heads, int nparts, float oscale) {
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
   const int d = threadIdx.x;
   const int C = heads * HD;
@@ -181,7 +200,7 @@ cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int 
       ll += pr[1] * c;
       oo += pr[2 + d] * c;
     }
-    out[static_cast<size_t>(b * Q + i) * C + h * HD + d] = oo / ll;
+    out[static_cast<size_t>(b * Q + i) * C + h * HD + d] = oo * oscale / ll;
   }
 }
 
@@ -201,7 +220,8 @@ size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S) {
 }
 
 int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
-               void* workspace, cudaStream_t stream) {
+               void* workspace, cudaStream_t stream, DropCfg drop, uint32_t drop_site) {
+  HH_REQUIRE(drop.thr == 0 || S % 8 == 0, "cross_attn: dropout needs a multiple of 8 keys");
   HH_REQUIRE(Q >= 1 && Q <= XQ, "cross_attn: 1..16 queries supported");
   HH_REQUIRE(ldkv % 8 == 0, "cross_attn: K/V row stride must be a multiple of 8 elements");
   HH_REQUIRE((reinterpret_cast<uintptr_t>(K) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 &&
@@ -219,9 +239,10 @@ int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* ou
     configured = true;
   }
   cross_attn_mma_kernel<<<B * heads * splits, XW * 32, smem, stream>>>(q, K, V, ldkv, static_cast<float*>(workspace), Q,
-                                                                      heads, S, splits, keys_per_warp);
+                                                                      heads, S, splits, keys_per_warp, drop, drop_site);
   HH_CHECK_LAUNCH("cross_attn_mma_kernel");
-  cross_merge_kernel<<<B * heads, HD, 0, stream>>>(static_cast<const float*>(workspace), out, Q, heads, nparts);
+  cross_merge_kernel<<<B * heads, HD, 0, stream>>>(static_cast<const float*>(workspace), out, Q, heads, nparts,
+                                                   drop.thr ? drop.scale : 1.f);
   HH_CHECK_LAUNCH("cross_merge_kernel");
   return 0;
 }

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
       float v = acc[i][j] + (a.bias ? a.bias[col] : 0.f);
       if (a.act == 1) v = fmaxf(v, 0.f);
       else if (a.act == 2) v = 1.f / (1.f + __expf(-v));
+      if (a.drop.thr) v *= drop_mult(a.drop, a.drop_site, static_cast<uint64_t>(row) * a.N + col);
       if (a.residual) v += a.residual[static_cast<size_t>(row) * a.ldres + col];
       a.out[static_cast<size_t>(row) * a.ldo + col] = v;
     }
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
 // ------------------------------------------------------------------------------------------ self attention
 __global__ void __launch_bounds__(32)
 self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
-                 float* __restrict__ out, int Q, int heads) {
+                 float* __restrict__ out, int Q, int heads, DropCfg drop, uint32_t drop_site) {
   __shared__ float Ks[16][HD + 1];
   __shared__ float Vs[16][HD + 1];
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
@@ -124,6 +125,12 @@ self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const
     l += s[j];
   }
   const float inv = 1.f / l;
+  if (drop.thr) {  // dropout on the normalised probabilities (nn.MultiheadAttention, training mode)
+    const uint64_t base = (static_cast<uint64_t>(blockIdx.x) * Q + lane) * Q;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < Q) s[j] *= drop_mult(drop, drop_site, base + j);
+  }
   float* o = out + static_cast<size_t>(b * Q + lane) * C + h * HD;
   for (int d = 0; d < HD; ++d) {
     float acc = 0.f;
@@ -347,9 +354,9 @@ int linear_f32(const LinArgs& a, cudaStream_t stream) {
 }
 
 int self_attn_queries(const float* q, const float* k, const float* v, int ld, float* out, int B, int Q, int heads,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, DropCfg drop, uint32_t drop_site) {
   HH_REQUIRE(Q >= 1 && Q <= 16, "self_attn_queries: 1..16 queries supported");
-  self_attn_kernel<<<B * heads, 32, 0, stream>>>(q, k, v, ld, out, Q, heads);
+  self_attn_kernel<<<B * heads, 32, 0, stream>>>(q, k, v, ld, out, Q, heads, drop, drop_site);
   HH_CHECK_LAUNCH("self_attn_kernel");
   return 0;
 }

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const LinBwdArgs a) {
       float v = 0.f;
       if (r0 + r < a.R && n0 + n < a.N) {
         v = a.dY[static_cast<size_t>(r0 + r) * a.ldy + n0 + n];
-        if (a.act) v = act_grad(v, a.Y[static_cast<size_t>(r0 + r) * a.ldyo + n0 + n], a.act);
+        if (a.drop.thr) v *= drop_mult(a.drop, a.drop_site, static_cast<uint64_t>(r0 + r) * a.N + n0 + n);
+        if (a.act) v = act_grad(v, a.Y[static_cast<size_t>(r0 + r) * a.ldyo + n0 + n], a.act) * (a.act_scale != 0.f ? a.act_scale : 1.f);
       }
       Gs[r][n] = v;
     }
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
       float v = 0.f;
       if (r0 + r < r_end && n0 + n < a.N) {
         v = a.dY[static_cast<size_t>(r0 + r) * a.ldy + n0 + n];
-        if (a.act) v = act_grad(v, a.Y[static_cast<size_t>(r0 + r) * a.ldyo + n0 + n], a.act);
+        if (a.drop.thr) v *= drop_mult(a.drop, a.drop_site, static_cast<uint64_t>(r0 + r) * a.N + n0 + n);
+        if (a.act) v = act_grad(v, a.Y[static_cast<size_t>(r0 + r) * a.ldyo + n0 + n], a.act) * (a.act_scale != 0.f ? a.act_scale : 1.f);
       }
       Gs[r][n] = v;
     }
@@ -258,7 +260,7 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int P, int n
 __global__ void __launch_bounds__(32)
 self_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
                      const float* __restrict__ dO, float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
-                     int ldg, int Q, int heads) {
+                     int ldg, int Q, int heads, DropCfg drop, uint32_t drop_site) {
   __shared__ float Qs[16][HD + 1], Ks[16][HD + 1], Vs[16][HD + 1], Gs[16][HD + 1];
   __shared__ float Ps[16][17], Ss[16][17];
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
@@ -286,16 +288,18 @@ self_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, c
       l += s[j];
     }
     const float inv = 1.f / l;
-    float dp[16], Dsum = 0.f;
+    // with dropout (training): O = sum_j (m_j p_j) v_j, m_j in {0, 1/(1-p)}: dP_j = m_j (dO . v_j), dV_j gets m_j p_j dO
+    float dp[16], mult[16], Dsum = 0.f;
     for (int j = 0; j < Q; ++j) {
       s[j] *= inv;
+      mult[j] = drop.thr ? drop_mult(drop, drop_site, (static_cast<uint64_t>(blockIdx.x) * Q + lane) * Q + j) : 1.f;
       float acc = 0.f;
       for (int d = 0; d < HD; ++d) acc += Gs[lane][d] * Vs[j][d];
-      dp[j] = acc;
-      Dsum += s[j] * acc;
+      dp[j] = acc * mult[j];
+      Dsum += s[j] * dp[j];
     }
     for (int j = 0; j < Q; ++j) {
-      Ps[lane][j] = s[j];
+      Ps[lane][j] = s[j] * mult[j];
       Ss[lane][j] = s[j] * (dp[j] - Dsum);
     }
     float* o = dq + static_cast<size_t>(b * Q + lane) * ldg + h * HD;
@@ -367,7 +371,8 @@ cross_stats_kernel(const float* __restrict__ q, const bf16* __restrict__ K, int 
 __global__ void __launch_bounds__(128)
 cross_keys_kernel(const float* __restrict__ q, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
                   const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ Dv,
-                  bf16* __restrict__ dK, bf16* __restrict__ dV, int lddkv, float* __restrict__ dS, int Q, int heads, int S) {
+                  bf16* __restrict__ dK, bf16* __restrict__ dV, int lddkv, float* __restrict__ dS, int Q, int heads, int S,
+                  DropCfg drop, uint32_t drop_site) {
   __shared__ float qs[16][HD], gs[16][HD];
   __shared__ float ls[16], ds_[16];
   const int h = blockIdx.y % heads, b = blockIdx.y / heads;
@@ -411,8 +416,11 @@ cross_keys_kernel(const float* __restrict__ q, const bf16* __restrict__ K, const
           dp += gs[i][d] * vf[d];
         }
         p[i] = __expf(s - ls[i]);
-        dsv[i] = p[i] * (dp - ds_[i]);
+        // dropout on the probabilities (training): dP = m (dO . v), dV weight = m p;  D_i = dO_i . O_i is unchanged
+        const float mult = drop.thr ? drop_mult(drop, drop_site, ((static_cast<uint64_t>(b) * heads + h) * Q + i) * S + j) : 1.f;
+        dsv[i] = p[i] * (mult * dp - ds_[i]);
         dS[((static_cast<size_t>(b) * heads + h) * Q + i) * S + j] = dsv[i];
+        p[i] *= mult;
       }
     }
   }
@@ -571,9 +579,9 @@ int ln_backward_rows(const LnBwdArgs& a, cudaStream_t s) {
 }
 
 int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const float* dO, float* dq, float* dk, float* dv,
-                  int ldg, int B, int Q, int heads, cudaStream_t s) {
+                  int ldg, int B, int Q, int heads, cudaStream_t s, DropCfg drop, uint32_t drop_site) {
   HH_REQUIRE(B > 0 && Q >= 1 && Q <= 16 && heads > 0, "self_attn_bwd: 1..16 queries");
-  self_attn_bwd_kernel<<<B * heads, 32, 0, s>>>(q, k, v, ld, dO, dq, dk, dv, ldg, Q, heads);
+  self_attn_bwd_kernel<<<B * heads, 32, 0, s>>>(q, k, v, ld, dO, dq, dk, dv, ldg, Q, heads, drop, drop_site);
   HH_CHECK_LAUNCH("self_attn_bwd_kernel");
   return 0;
 }
@@ -583,7 +591,8 @@ size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S) {
 }
 
 int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
-                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s) {
+                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
+                   DropCfg drop, uint32_t drop_site) {
   HH_REQUIRE(B > 0 && Q >= 1 && Q <= 16 && heads > 0 && S > 0, "cross_attn_bwd: 1..16 queries");
   HH_REQUIRE(q && K && V && O && dO && dq && dK && dV && workspace, "cross_attn_bwd: null buffer");
   HH_REQUIRE(ldkv % 8 == 0 && lddkv % 2 == 0, "cross_attn_bwd: row pitch");
@@ -592,7 +601,7 @@ int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const
   float* dS = Dv + static_cast<size_t>(B) * heads * Q;
   cross_stats_kernel<<<B * heads, 32 * Q, 0, s>>>(q, K, ldkv, dO, O, lse, Dv, Q, heads, S);
   dim3 grid((S + 127) / 128, B * heads);
-  cross_keys_kernel<<<grid, 128, 0, s>>>(q, K, V, ldkv, dO, lse, Dv, dK, dV, lddkv, dS, Q, heads, S);
+  cross_keys_kernel<<<grid, 128, 0, s>>>(q, K, V, ldkv, dO, lse, Dv, dK, dV, lddkv, dS, Q, heads, S, drop, drop_site);
   cross_dq_kernel<<<B * heads, 256, 0, s>>>(dS, K, ldkv, dq, Q, heads, S);
   HH_CHECK_LAUNCH("cross_attn_bwd kernels");
   return 0;

@@ -453,10 +453,12 @@ int Decoder::pack(cudaStream_t s) {
 }
 
 static int lin(const float* in, int ldi, const float* in_add, int add_mod, const float* W, const float* bias,
-               const float* residual, int ldres, float* out, int ldo, int R, int N, int K, int act, cudaStream_t s) {
+               const float* residual, int ldres, float* out, int ldo, int R, int N, int K, int act, cudaStream_t s,
+               DropCfg drop = drop_off(), uint32_t drop_site = 0) {
   LinArgs la{};
   la.in = in; la.ldi = ldi; la.in_add = in_add; la.add_mod = add_mod; la.W = W; la.bias = bias;
   la.residual = residual; la.ldres = ldres; la.out = out; la.ldo = ldo; la.R = R; la.N = N; la.K = K; la.act = act;
+  la.drop = drop; la.drop_site = drop_site;
   return linear_f32(la, s);
 }
 
@@ -518,6 +520,11 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
       saved_T = T;
     }
   }
+  // dropout sites of TransformerDecoderLayer.forward_pre in training mode (tfm_decoder.py:372-386,431-459): site =
+  // layer * 8 + {0 self-attention probabilities, 1 dropout1, 2 cross-attention probabilities, 3 dropout2, 4 FFN inner
+  // dropout, 5 dropout3}.  Only the training forward drops; backward() regenerates the masks from saved_drop.
+  const DropCfg dr = save ? next_drop : drop_off();
+  if (save) saved_drop = dr;
 
   // proj (no bias, :200) -> pre_norm (:86) ; memory and memory+pos in bf16 for the K/V GEMMs
   PROF(K_DEC_GEMM, cast_rows_bf16(features, stride_b, stride_row, S, feat, static_cast<int>(BS), F, s));
@@ -552,23 +559,23 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
     PROF(K_DEC_QUERY, lnq(A.x0, p + "norm1", A.n1));
     PROF(K_DEC_QUERY, lin(A.n1, C, qpos, Q, wsa, bsa, nullptr, 0, A.qkv, 3 * C, R, 2 * C, C, 0, s));                   // q,k <- n1+qpos
     PROF(K_DEC_QUERY, lin(A.n1, C, nullptr, 0, wsa + static_cast<size_t>(2) * C * C, bsa + 2 * C, nullptr, 0, A.qkv + 2 * C, 3 * C, R, C, C, 0, s));
-    PROF(K_DEC_QUERY, self_attn_queries(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, A.o1, B, Q, heads, s));
+    PROF(K_DEC_QUERY, self_attn_queries(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, A.o1, B, Q, heads, s, dr, i * 8 + 0));
     PROF(K_DEC_QUERY, lin(A.o1, C, nullptr, 0, weights.get(p + "self_attn.out_proj.weight"), weights.get(p + "self_attn.out_proj.bias"), A.x0, C,
-           A.x1, C, R, C, C, 0, s));
+           A.x1, C, R, C, C, 0, s, dr, i * 8 + 1));
     // cross attention to the patch tokens (:436-441,456)
     PROF(K_DEC_QUERY, lnq(A.x1, p + "norm2", A.n2));
     PROF(K_DEC_QUERY, lin(A.n2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
            static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, A.qc, C, R, C, C, 0, s));
     PROF(K_DEC_CROSS, cross_attn(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, B, Q, heads, S,
-                  ws_cross.ptr, s));
+                  ws_cross.ptr, s, dr, i * 8 + 2));
     PROF(K_DEC_QUERY, lin(A.o2, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
-           A.x1, C, A.x2, C, R, C, C, 0, s));
+           A.x1, C, A.x2, C, R, C, C, 0, s, dr, i * 8 + 3));
     // FFN (:457-459)
     PROF(K_DEC_QUERY, lnq(A.x2, p + "norm3", A.n3));
     PROF(K_DEC_QUERY, lin(A.n3, C, nullptr, 0, weights.get(p + "linear1.weight"), weights.get(p + "linear1.bias"), nullptr, 0, A.f, Fd, R, Fd, C,
-           1, s));
+           1, s, dr, i * 8 + 4));
     PROF(K_DEC_QUERY, lin(A.f, Fd, nullptr, 0, weights.get(p + "linear2.weight"), weights.get(p + "linear2.bias"), A.x2, C, A.x3, C, R, C, Fd, 0,
-           s));
+           s, dr, i * 8 + 5));
     // intermediate output through the shared final norm (:282,287-291)
     PROF(K_DEC_QUERY, lnq(A.x3, "transformer.decoder.norm", hs + static_cast<size_t>(i) * R * C));
     launches += 15;

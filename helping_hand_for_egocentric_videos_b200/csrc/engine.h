@@ -98,6 +98,9 @@ struct Decoder {
   };
   std::vector<LayerBufs> saved;
   int saved_B = 0, saved_T = 0;
+  // dropout of the training forward (hh_decoder_set_dropout): `next_drop` applies to the next forward(save = true),
+  // `saved_drop` is what that forward used -- backward() regenerates the same masks from it
+  DropCfg next_drop = drop_off(), saved_drop = drop_off();
   float *sv_cond = nullptr, *sv_x1 = nullptr, *sv_x2 = nullptr, *sv_hsproj = nullptr;
   DevBuf ws_train, w_kallT, w_vallT;
   DevBuf bw_a, bw_b, bw_c, bw_d, bw_dk, bw_dv, bw_t1, bw_t2, bw_t3, bw_ws;
@@ -106,7 +109,7 @@ struct Decoder {
   explicit Decoder(const hh_decoder_cfg& c);
   static int validate(const hh_decoder_cfg& c);
   int pack(cudaStream_t s);
-  // save = true keeps every layer's activations for backward() (training forward; eval-mode arithmetic, no dropout)
+  // save = true keeps every layer's activations for backward() (training forward; dropout per next_drop)
   int forward(const float* features, int64_t stride_b, int64_t stride_row, int B, int T, float* hs, float* logits,
               float* boxes, cudaStream_t s, bool save = false);
   // Gradients of all decoder parameters for upstream d_hs [L,B,Q,C] and d_boxes [L,B*Tb,Q,4] (either may be null = 0);

@@ -65,18 +65,21 @@ __global__ void pos3d_bwd_kernel(const float* __restrict__ dpos, float* __restri
 }
 
 int dgrad(const float* dY, int ldy, const float* Y, int ldyo, int act, const float* W, float* dX, int lddx, int R, int N,
-          int K, float beta, cudaStream_t s) {
+          int K, float beta, cudaStream_t s, DropCfg drop = drop_off(), uint32_t drop_site = 0, float act_scale = 1.f) {
   LinBwdArgs a{};
   a.dY = dY; a.ldy = ldy; a.Y = Y; a.ldyo = ldyo; a.act = act; a.W = W; a.dX = dX; a.lddx = lddx; a.R = R; a.N = N; a.K = K;
   a.beta = beta; a.scale = 1.f;
+  a.drop = drop; a.drop_site = drop_site; a.act_scale = act_scale;
   return linear_dgrad_f32(a, s);
 }
 
 int wgrad(const float* dY, int ldy, const float* Y, int ldyo, int act, const float* X, int ldx, const float* x_add,
-          int add_mod, float* dW, int ldw, float* db, int R, int N, int K, float beta, float scale, cudaStream_t s) {
+          int add_mod, float* dW, int ldw, float* db, int R, int N, int K, float beta, float scale, cudaStream_t s,
+          DropCfg drop = drop_off(), uint32_t drop_site = 0, float act_scale = 1.f) {
   LinBwdArgs a{};
   a.dY = dY; a.ldy = ldy; a.Y = Y; a.ldyo = ldyo; a.act = act; a.X = X; a.ldx = ldx; a.x_add = x_add; a.add_mod = add_mod;
   a.dW = dW; a.ldw = ldw; a.db = db; a.R = R; a.N = N; a.K = K; a.beta = beta; a.scale = scale;
+  a.drop = drop; a.drop_site = drop_site; a.act_scale = act_scale;
   return linear_wgrad_f32(a, s);
 }
 
@@ -186,6 +189,7 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
 
   // =========================================================================================== decoder layers
   HH_CHECK_CUDA(cudaMemsetAsync(dx, 0, RC_ * 4, s));  // gradient w.r.t. the residual stream after the current layer
+  const DropCfg dr = saved_drop;   // the masks of the matching forward, regenerated
   auto ln_bwd = [&](const float* x, const std::string& nm, const float* dy, float beta_w) {
     LnBwdArgs a{};
     a.x = x; a.ldx = C; a.w = weights.get(nm + ".weight"); a.eps = 1e-5f; a.dy = dy; a.lddy = C;
@@ -200,18 +204,24 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     const float* wsa = static_cast<const float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C;
     // hs_i = norm(x3): its gradient joins the stream (the norm's weights are shared by all layers: accumulate)
     RC(ln_bwd(A.x3, "transformer.decoder.norm", dhs + static_cast<size_t>(i) * RC_, i == Lr - 1 ? 0.f : 1.f));
-    // ---- FFN: x3 = x2 + relu(n3 W1^T + b1) W2^T + b2
-    RC(wgrad(dx, C, nullptr, 0, 0, A.f, Fd, nullptr, 0, G(p + "linear2.weight"), Fd, G(p + "linear2.bias"), R, C, Fd, 0.f, 1.f, s));
-    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "linear2.weight"), ga, Fd, R, C, Fd, 0.f, s));              // ga = d f
-    RC(wgrad(ga, Fd, A.f, Fd, 1, A.n3, C, nullptr, 0, G(p + "linear1.weight"), C, G(p + "linear1.bias"), R, Fd, C, 0.f, 1.f, s));
-    RC(dgrad(ga, Fd, A.f, Fd, 1, weights.get(p + "linear1.weight"), tmp, C, R, Fd, C, 0.f, s));                // tmp = d n3
+    // ---- FFN: x3 = x2 + drop3(drop(relu(n3 W1^T + b1)) W2^T + b2).  A.f is the hidden AFTER its dropout, so
+    // f > 0 <=> (ReLU active and kept) and the inner dropout is only the factor 1/(1-p) on the ReLU derivative
+    const uint32_t st0 = static_cast<uint32_t>(i) * 8;
+    const float fscale = dr.thr ? dr.scale : 1.f;
+    RC(wgrad(dx, C, nullptr, 0, 0, A.f, Fd, nullptr, 0, G(p + "linear2.weight"), Fd, G(p + "linear2.bias"), R, C, Fd, 0.f, 1.f, s,
+             dr, st0 + 5));
+    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "linear2.weight"), ga, Fd, R, C, Fd, 0.f, s, dr, st0 + 5));  // ga = d f
+    RC(wgrad(ga, Fd, A.f, Fd, 1, A.n3, C, nullptr, 0, G(p + "linear1.weight"), C, G(p + "linear1.bias"), R, Fd, C, 0.f, 1.f, s,
+             drop_off(), 0, fscale));
+    RC(dgrad(ga, Fd, A.f, Fd, 1, weights.get(p + "linear1.weight"), tmp, C, R, Fd, C, 0.f, s, drop_off(), 0, fscale));  // tmp = d n3
     RC(ln_bwd(A.x2, p + "norm3", tmp, 0.f));
     // ---- cross attention: x2 = x1 + CA(qc, K_i, V_i) Wo^T + bo,  qc = s ((n2 + qpos) Wq^T + bq)
     RC(wgrad(dx, C, nullptr, 0, 0, A.o2, C, nullptr, 0, G(p + "multihead_attn.out_proj.weight"), C,
-             G(p + "multihead_attn.out_proj.bias"), R, C, C, 0.f, 1.f, s));
-    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "multihead_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s));  // tmp = d o2
+             G(p + "multihead_attn.out_proj.bias"), R, C, C, 0.f, 1.f, s, dr, st0 + 3));
+    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "multihead_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s, dr, st0 + 3));  // tmp = d o2
     RC(cross_attn_bwd(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, tmp, tmp2,
-                      dKall + static_cast<size_t>(i) * C, dVall + static_cast<size_t>(i) * C, Lr * C, B, Q, heads, S, bw_ws.ptr, s));
+                      dKall + static_cast<size_t>(i) * C, dVall + static_cast<size_t>(i) * C, Lr * C, B, Q, heads, S, bw_ws.ptr, s,
+                      dr, st0 + 2));
     float* dWca = G(p + "multihead_attn.in_proj_weight");
     float* dbca = G(p + "multihead_attn.in_proj_bias");
     RC(wgrad(tmp2, C, nullptr, 0, 0, A.n2, C, qpos, Q, dWca, C, dbca, R, C, C, 0.f, qscale, s));                // rows [0, C): Wq
@@ -221,9 +231,9 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     RC(ln_bwd(A.x1, p + "norm2", tmp, 0.f));
     // ---- self attention: x1 = x0 + SA(q, k, v) Wo^T + bo;  q, k from n1 + qpos, v from n1
     RC(wgrad(dx, C, nullptr, 0, 0, A.o1, C, nullptr, 0, G(p + "self_attn.out_proj.weight"), C, G(p + "self_attn.out_proj.bias"),
-             R, C, C, 0.f, 1.f, s));
-    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "self_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s));     // tmp = d o1
-    RC(self_attn_bwd(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, tmp, dqkv, dqkv + C, dqkv + 2 * C, 3 * C, B, Q, heads, s));
+             R, C, C, 0.f, 1.f, s, dr, st0 + 1));
+    RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "self_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s, dr, st0 + 1));  // tmp = d o1
+    RC(self_attn_bwd(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, tmp, dqkv, dqkv + C, dqkv + 2 * C, 3 * C, B, Q, heads, s, dr, st0 + 0));
     float* dWsa = G(p + "self_attn.in_proj_weight");
     float* dbsa = G(p + "self_attn.in_proj_bias");
     RC(wgrad(dqkv, 3 * C, nullptr, 0, 0, A.n1, C, qpos, Q, dWsa, C, dbsa, R, C, C, 0.f, qscale, s));            // Wq (pre-scaled q)

@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "hh_rng.cuh"
+
 namespace hh {
 
 typedef __nv_bfloat16 bf16;
@@ -107,16 +109,19 @@ struct LinArgs {
   int R, N, K;
   int act;                                // 0 none, 1 relu, 2 sigmoid
   int in_relu;                            // 1: apply ReLU to the input first (txt_proj = ReLU -> Linear)
+  DropCfg drop; uint32_t drop_site;       // training: dropout on act(x W^T + b) before the residual add, idx = row*N + col
 };
 int linear_f32(const LinArgs& a, cudaStream_t stream);
 // Query self-attention: q,k,v fp32 [B*Q, C] (q pre-scaled), heads of 64 -> out fp32 [B*Q, C].
+// drop: dropout on the attention probabilities (training), idx = ((b*heads + h)*Q + i)*Q + j
 int self_attn_queries(const float* q, const float* k, const float* v, int ld, float* out, int B, int Q, int heads,
-                      cudaStream_t stream);
+                      cudaStream_t stream, DropCfg drop = drop_off(), uint32_t drop_site = 0);
 // Query -> patch cross attention. q fp32 [B*Q, C] (pre-scaled); K,V bf16 rows [B*S] with row stride ldkv, head h at
 // column h*64.  Output fp32 [B*Q, C].  workspace: see cross_attn_workspace_bytes.
 size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S);
+// drop: dropout on the attention probabilities (training), idx = ((b*heads + h)*Q + i)*S + j
 int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
-               void* workspace, cudaStream_t stream);
+               void* workspace, cudaStream_t stream, DropCfg drop = drop_off(), uint32_t drop_site = 0);
 size_t cross_attn_simt_workspace_bytes(int B, int Q, int heads, int S);
 int cross_attn_simt(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
                     void* workspace, cudaStream_t stream);
@@ -153,6 +158,8 @@ struct LinBwdArgs {
   int R, N, K;
   float beta, scale;
   int rows_per_split;   // set by linear_wgrad_f32
+  DropCfg drop; uint32_t drop_site;   // the forward dropped act(.) [R, N] (idx = row*N + col): g = act'(dY * mult, Y)
+  float act_scale;                    // 0 = 1; extra factor on act'(.) (ReLU followed by dropout: kept <=> Y > 0)
 };
 int linear_dgrad_f32(const LinBwdArgs& a, cudaStream_t s);
 int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s);
@@ -171,11 +178,12 @@ size_t ln_backward_workspace_bytes(int M, int D);
 int ln_backward_rows(const LnBwdArgs& a, cudaStream_t s);
 // backward of self_attn_queries: dq/dk/dv rows have stride ldg (same packing as the forward's q/k/v with stride ld)
 int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const float* dO, float* dq, float* dk, float* dv,
-                  int ldg, int B, int Q, int heads, cudaStream_t s);
+                  int ldg, int B, int Q, int heads, cudaStream_t s, DropCfg drop = drop_off(), uint32_t drop_site = 0);
 // backward of cross_attn: dq fp32 [B*Q, C]; dK, dV bf16 rows [B*S] with stride lddkv (head h at column h*64)
 size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S);
 int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
-                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s);
+                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
+                   DropCfg drop = drop_off(), uint32_t drop_site = 0);
 // out[c] = beta*out[c] + sum_r X[r, c]  (X fp32 or bf16, row stride ld); workspace colsum_workspace_bytes(cols)
 size_t colsum_workspace_bytes(long long cols);
 int colsum_rows(const void* X, int is_bf16, long long ld, long long rows, long long cols, float beta, float* out,

@@ -6,8 +6,9 @@
     out, hs, attn, self_attn = model(video_grid)        # run/test_EgoMCQ.py:73 ; attn == self_attn == []
 
 The module tree holds parameters; ``ObjDecoder.forward`` (reference :183-233) is one C-ABI call (hh_decoder_forward)
-and the small projection heads are hh_linear_f32 calls.  Inference semantics: dropout (p=0.1 in the reference's
-training mode) is not applied and no autograd graph is recorded -- decoder training is SURVEY.md section 8f row 2.
+and the small projection heads are hh_linear_f32 calls.  In ``train()`` mode the reference's dropout (nn.Dropout x4
+per layer and the attention-probability dropout of both nn.MultiheadAttention modules, p = ``dropout``) is applied by
+the engine's training forward with counter-based masks (hh_decoder_set_dropout); ``eval()`` is the inference arithmetic.
 """
 from __future__ import annotations
 
@@ -222,7 +223,11 @@ class ObjDecoder(nn.Module):
                                  1 if pred_traj else 0)
         self._handle = None
         self._sync = _ParamSync()
-        self._warned_train = False
+        # dropout stream of the training forward: seed (None -> torch.initial_seed(), i.e. torch.manual_seed governs it)
+        # and a per-module step counter; `last_dropout` records what the most recent forward used (None = no dropout)
+        self.dropout_seed = None
+        self._drop_step = 0
+        self.last_dropout = None
 
     # -- engine plumbing ---------------------------------------------------------------------------------------
     def _engine(self):
@@ -294,6 +299,15 @@ class ObjDecoder(nn.Module):
         logits = torch.empty(L_, B * (4 if traj else 1), Q, ncls, dtype=torch.float32, device=dev)
         boxes = torch.empty(L_, B * (T if traj else 1), Q, 4, dtype=torch.float32, device=dev)
         fn = L.load().hh_decoder_forward_train if train else L.load().hh_decoder_forward
+        self.last_dropout = None
+        if train:
+            p = float(self.transformer.dropout_p) if self.training else 0.0
+            seed = int(self.dropout_seed if self.dropout_seed is not None else torch.initial_seed()) & ((1 << 64) - 1)
+            offset = self._drop_step & 0xFFFFFFFF
+            L.check(L.load().hh_decoder_set_dropout(self._engine(), p, seed, offset), "hh_decoder_set_dropout")
+            if p > 0:
+                self.last_dropout = {"p": p, "seed": seed, "offset": offset}
+                self._drop_step += 1
         L.check(fn(self._engine(), features.data_ptr(), features.stride(0), features.stride(2), B, T, L.ptr(hs),
                    L.ptr(logits), L.ptr(boxes), L.stream_ptr()), "hh_decoder_forward")
         return hs, logits, boxes
@@ -304,10 +318,6 @@ class ObjDecoder(nn.Module):
         backward (gradients for every decoder parameter; `features` come from the frozen backbone and get none)."""
         if not features.is_cuda:
             raise RuntimeError("ObjDecoder (B200): input is on %s; there is no CPU fallback" % features.device)
-        if self.training and self.transformer.dropout_p > 0 and not self._warned_train:
-            warnings.warn("ObjDecoder (B200): dropout (p=%.2f in the reference's training mode) is not applied; the "
-                          "forward and its gradients are those of eval mode" % self.transformer.dropout_p)
-            self._warned_train = True
         B, T, n, F = features.shape
         if n != self.patches_per_frame or F != self._cfg.feature_dim:
             raise RuntimeError("expected features [B,T,%d,%d], got %s" % (self.patches_per_frame, self._cfg.feature_dim,
@@ -323,8 +333,8 @@ class ObjDecoder(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             hs, logits, boxes = _DecoderFn.apply(self, features, *params)
         else:
-            with torch.no_grad():
-                hs, logits, boxes = self._run_engine(features, train=False)
+            with torch.no_grad():  # train() mode drops activations even when no gradient is recorded, as nn.Dropout does
+                hs, logits, boxes = self._run_engine(features, train=self.training and self.transformer.dropout_p > 0)
         out = {'pred_logits': logits[-1], 'pred_boxes': boxes[-1]}
         if self.aux_loss:
             out['aux_outputs'] = [{'pred_logits': a, 'pred_boxes': b} for a, b in zip(logits[:-1], boxes[:-1])]

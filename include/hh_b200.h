@@ -96,14 +96,19 @@ int hh_decoder_set_weight(hh_decoder* dec, const char* key, const float* data, i
  */
 int hh_decoder_forward(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
                        float* hs, float* logits, float* boxes, void* stream);
-/* Training: the same forward that also keeps every layer's activations inside the engine (eval-mode arithmetic: the
- * reference's dropout 0.1, tfm_decoder.py:52, is not applied), then hh_decoder_backward differentiates it.
+/* Training: the same forward that also keeps every layer's activations inside the engine, then hh_decoder_backward
+ * differentiates it.  Dropout of the reference's training mode (nn.Dropout x4 per layer, tfm_decoder.py:372-386, and
+ * nn.MultiheadAttention(dropout=p) on the self- and cross-attention probabilities, :365-366) is applied by the training
+ * forward when hh_decoder_set_dropout was called with p > 0: masks come from a counter-based generator (Philox4x32-10,
+ * keyed by `seed`, stream position `offset`; csrc/hh_rng.cuh), so hh_decoder_backward regenerates them instead of storing
+ * them.  The setting persists until changed; callers advance `offset` every step.  p = 0 (the default) = eval arithmetic.
  * hh_decoder_backward: hs / boxes are the outputs of that forward; d_hs [L,B,Q,C] and d_boxes [L,B*Tb,Q,4] are the
  * upstream gradients (either may be NULL = zero).  Class logits carry no gradient (the reference criterion has no class
  * loss, run/train.py:471, exclude_class=True): class_embed.* get zeros.  Gradients of every parameter key are then read
  * with hh_decoder_get_grad (fp32, `numel` elements, device memory). */
 int hh_decoder_forward_train(hh_decoder* dec, const float* features, int64_t stride_b, int64_t stride_row, int B, int T,
                              float* hs, float* logits, float* boxes, void* stream);
+int hh_decoder_set_dropout(hh_decoder* dec, float p, uint64_t seed, uint32_t offset);
 int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, const float* d_hs, const float* d_boxes,
                         void* stream);
 int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream);

@@ -297,9 +297,51 @@ def clip_forward(video: Tensor, tokens: Optional[Tensor], sd, heads: int, text_h
 # object-aware decoder  (model/tfm_decoder.py)
 # --------------------------------------------------------------------------------------------
 
-def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, w, b, wo, bo, heads: int) -> Tensor:
-    """nn.MultiheadAttention forward (batch-first here), eval mode, no masks
-    (call sites model/tfm_decoder.py:433-441)."""
+def philox_keep(seed: int, offset: int, site: int, numel: int, p: float) -> Tensor:
+    """Dropout multipliers (0 or 1/(1-p)) of one dropout site of the decoder's training forward, element order =
+    row-major order of the dropped tensor.  Restates csrc/hh_rng.cuh (Philox4x32-10, key = seed, counter =
+    (idx >> 3, site, offset), 16-bit lane idx & 7, keep <=> lane >= round(p * 65536)) so that the reference graph can be
+    run with the masks the CUDA path draws.  The DISTRIBUTION is nn.Dropout's / F.dropout's (model/tfm_decoder.py:
+    372-386; nn.MultiheadAttention(dropout=p) :365-366); the random stream is this project's, not torch's."""
+    import numpy as np
+    idx = np.arange(numel, dtype=np.uint64)
+    blk = idx >> np.uint64(3)
+    M32 = np.uint64(0xFFFFFFFF)
+    c0 = blk & M32
+    c1 = (blk >> np.uint64(32)) & M32
+    c2 = np.full(numel, site, dtype=np.uint64)
+    c3 = np.full(numel, offset, dtype=np.uint64)
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c0
+        p1 = np.uint64(0xCD9E8D57) * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & M32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & M32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & M32, lo1, (hi0 ^ c3 ^ k1) & M32, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M32
+    words = np.stack([c0, c1, c2, c3], 1)                                  # [numel, 4]
+    lane = (idx & np.uint64(7)).astype(np.int64)
+    w = words[np.arange(numel), lane >> 1]
+    r = (w >> (np.uint64(16) * (lane & 1).astype(np.uint64))) & np.uint64(0xFFFF)
+    thr = max(1, int(p * 65536.0 + 0.5))
+    keep = (r >= np.uint64(thr)).astype(np.float32) * np.float32(1.0 / (1.0 - p))
+    return torch.from_numpy(keep)
+
+
+def _drop(x: Tensor, dropout, site: int) -> Tensor:
+    """F.dropout(x, p, training=True) with the mask of philox_keep (dropout = None: eval mode, identity)."""
+    if dropout is None or dropout["p"] <= 0:
+        return x
+    m = philox_keep(dropout["seed"], dropout["offset"], site, x.numel(), dropout["p"])
+    return x * m.view(x.shape).to(x.dtype)
+
+
+def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, w, b, wo, bo, heads: int, dropout=None, site: int = 0) -> Tensor:
+    """nn.MultiheadAttention forward (batch-first here), no masks (call sites model/tfm_decoder.py:433-441).
+    dropout = None: eval mode; otherwise the attention probabilities are dropped after the softmax, as
+    F.multi_head_attention_forward does in training mode."""
     C = q_in.shape[-1]
     hd = C // heads
     q = F.linear(q_in, w[:C], b[:C])
@@ -310,7 +352,7 @@ def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, w, b, wo, bo, heads: int) -> 
     q = q.view(B, Lq, heads, hd).transpose(1, 2) * (hd ** -0.5)
     k = k.view(B, Lk, heads, hd).transpose(1, 2)
     v = v.view(B, Lk, heads, hd).transpose(1, 2)
-    o = torch.softmax(q @ k.transpose(-1, -2), -1) @ v
+    o = _drop(torch.softmax(q @ k.transpose(-1, -2), -1), dropout, site) @ v           # probs [B, heads, Lq, Lk]
     return F.linear(o.transpose(1, 2).reshape(B, Lq, C), wo, bo)
 
 
@@ -324,10 +366,13 @@ def decoder_pos_embed(sd, T: int) -> Tensor:
 
 
 def decoder_forward(features: Tensor, sd, heads: int = 8, pred_traj: bool = True,
-                    num_frames: Optional[int] = None):
+                    num_frames: Optional[int] = None, dropout=None):
     """ObjDecoder.forward (model/tfm_decoder.py:183-233) with Cross_Attention.forward (:76-93),
     TransformerDecoder.forward (:255-295) and TransformerDecoderLayer.forward_pre (:420-461, sa_first).
-    features [B,T,n,F] -> (out, hs[L,B,Q,C], [], [])."""
+    features [B,T,n,F] -> (out, hs[L,B,Q,C], [], []).
+    dropout = {"p", "seed", "offset"}: training mode -- dropout1/2/3, the FFN's inner dropout (:372-386) and the
+    attention-probability dropout of both nn.MultiheadAttention modules, with the masks of philox_keep
+    (site = layer * 8 + {0 self-attn probs, 1 dropout1, 2 cross-attn probs, 3 dropout2, 4 FFN inner, 5 dropout3})."""
     B, T, n, _ = features.shape
     C = sd["proj.weight"].shape[0]
     mem = F.linear(features, sd["proj.weight"]).reshape(B, T * n, C)                                  # :200
@@ -343,15 +388,16 @@ def decoder_forward(features: Tensor, sd, heads: int = 8, pred_traj: bool = True
     for i in range(L):
         p = "transformer.decoder.layers.%d." % i
         t2 = lnf(tgt, p + "norm1")
-        tgt = tgt + _mha(t2 + qpos, t2 + qpos, t2, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
-                         sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], heads)
+        tgt = tgt + _drop(_mha(t2 + qpos, t2 + qpos, t2, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                               sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], heads,
+                               dropout, 8 * i + 0), dropout, 8 * i + 1)                              # :431-435
         t2 = lnf(tgt, p + "norm2")
-        tgt = tgt + _mha(t2 + qpos, mem + pos, mem, sd[p + "multihead_attn.in_proj_weight"],
-                         sd[p + "multihead_attn.in_proj_bias"], sd[p + "multihead_attn.out_proj.weight"],
-                         sd[p + "multihead_attn.out_proj.bias"], heads)
+        tgt = tgt + _drop(_mha(t2 + qpos, mem + pos, mem, sd[p + "multihead_attn.in_proj_weight"],
+                               sd[p + "multihead_attn.in_proj_bias"], sd[p + "multihead_attn.out_proj.weight"],
+                               sd[p + "multihead_attn.out_proj.bias"], heads, dropout, 8 * i + 2), dropout, 8 * i + 3)  # :438-456
         t2 = lnf(tgt, p + "norm3")
-        tgt = tgt + F.linear(F.relu(F.linear(t2, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
-                             sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+        ff = _drop(F.relu(F.linear(t2, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), dropout, 8 * i + 4)
+        tgt = tgt + _drop(F.linear(ff, sd[p + "linear2.weight"], sd[p + "linear2.bias"]), dropout, 8 * i + 5)   # :457-459
         hs.append(lnf(tgt, "transformer.decoder.norm"))                                               # :282
     hs = torch.stack(hs)                                                                              # [L,B,Q,C]
     logits = F.linear(hs, sd["class_embed.weight"], sd["class_embed.bias"])                           # :208

@@ -95,9 +95,11 @@ def test_cross_attention_backward(B, Q, heads, S):
 
 
 # ------------------------------------------------------------------------------------------ whole-decoder backward
-def _decoder_grads_case(cfg, B, seed):
+def _decoder_grads_case(cfg, B, seed, dropout_p=0.0):
     """Gradients of a random linear functional of (hs, all layers' boxes, obj_proj embeddings) w.r.t. every decoder
-    parameter: hand-written backward (hh_decoder_backward via autograd.Function) against autograd through the oracle."""
+    parameter: hand-written backward (hh_decoder_backward via autograd.Function) against autograd through the oracle.
+    dropout_p > 0: the module runs in train() mode (the reference's training mode, dropout at six sites per layer) and
+    the oracle graph is run with the very masks the engine drew (oracle philox_keep restates csrc/hh_rng.cuh)."""
     from oracle import hh_oracle as O
     from helping_hand_for_egocentric_videos_b200.model import tfm_decoder as D
     c = cfg
@@ -111,25 +113,35 @@ def _decoder_grads_case(cfg, B, seed):
     w_box = torch.randn(c["layers"], B * Tb, c["Q"], 4, generator=g)
     w_emb = torch.randn(B, c["Q"], 256, generator=g)
 
-    # oracle side
-    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    out, hs, _, _ = O.decoder_forward(feats, ref, heads=c["heads"], pred_traj=c["pred_traj"])
-    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
-    loss = (hs * w_hs).sum() + (boxes * w_box).sum() + (O.obj_proj(hs[-1], ref) * w_emb).sum()
-    loss.backward()
-
     # CUDA side
     tr = D.Cross_Attention(d_model=c["C"], nhead=c["heads"], num_decoder_layers=c["layers"], dim_feedforward=c["ffn"],
-                           normalize_before=True, return_intermediate_dec=True)
+                           dropout=dropout_p if dropout_p > 0 else 0.1, normalize_before=True, return_intermediate_dec=True)
     dec = D.ObjDecoder(transformer=tr, num_classes=c["ncls"], num_queries=c["Q"], aux_loss=True, pred_traj=c["pred_traj"],
                        feature_dim=c["F"], num_frames=c["T"], patches_per_frame=c["n"])
     dec.load_state_dict(sd, strict=True)
-    dec = dec.cuda().eval()                 # eval: the reference's dropout would be active in train()
+    dec = dec.cuda()
+    if dropout_p > 0:
+        dec.train()
+        dec.dropout_seed = 0x1234ABCD5678 + seed
+        dec._drop_step = 3
+    else:
+        dec.eval()                          # eval: the inference arithmetic, no dropout
     o2, hs2, _, _ = dec(feats.cuda())
     boxes2 = torch.stack([a["pred_boxes"] for a in o2["aux_outputs"]] + [o2["pred_boxes"]])
     loss2 = (hs2 * w_hs.cuda()).sum() + (boxes2 * w_box.cuda()).sum() + (dec.obj_proj(hs2[-1]) * w_emb.cuda()).sum()
     loss2.backward()
+    drop = dec.last_dropout
+    assert (drop is not None) == (dropout_p > 0)
+
+    # oracle side (same dropout masks)
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out, hs, _, _ = O.decoder_forward(feats, ref, heads=c["heads"], pred_traj=c["pred_traj"], dropout=drop)
+    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+    loss = (hs * w_hs).sum() + (boxes * w_box).sum() + (O.obj_proj(hs[-1], ref) * w_emb).sum()
+    loss.backward()
     assert abs(loss2.item() - loss.item()) <= 2e-2 * max(1.0, abs(loss.item()))
+    hs_err = (hs2.detach().cpu() - hs.detach()).abs().max().item()
+    assert hs_err <= 3e-2, hs_err             # a single mismatched mask element would show up at the 0.1 .. 1 level
     return ref, dict(dec.named_parameters())
 
 
@@ -179,3 +191,56 @@ def test_decoder_backward_c4_geometry():
     cfg = dict(C=512, heads=8, layers=6, ffn=2048, Q=13, n=256, T=4, F=1024, ncls=63, pred_traj=True)
     ref, params = _decoder_grads_case(cfg, 3, 77)
     _check_grads(ref, params)
+
+
+# ------------------------------------------------------------------------------------------ training-mode dropout
+@pytest.mark.parametrize("name", ["dec_tiny_traj", "dec_tiny_notraj"])
+def test_decoder_dropout_forward_backward_tiny(name):
+    """train() mode, p = 0.1 (the reference's Cross_Attention default): outputs and every parameter gradient against the
+    oracle graph run with the same masks."""
+    from oracle import golden_cases as gc
+    case = gc.CASES[name]
+    B = 2 if name == "dec_tiny_traj" else 4
+    ref, params = _decoder_grads_case(case["cfg"], B, case["seed"], dropout_p=0.1)
+    _check_grads(ref, params, tol_cos=0.99, tol_rel=0.15)
+
+
+def test_decoder_dropout_c4_geometry():
+    """BASELINE c4 decoder geometry in training mode with dropout 0.1 (run/train.py trains the decoder in train())."""
+    cfg = dict(C=512, heads=8, layers=6, ffn=2048, Q=13, n=256, T=4, F=1024, ncls=63, pred_traj=True)
+    ref, params = _decoder_grads_case(cfg, 3, 78, dropout_p=0.1)
+    _check_grads(ref, params)
+
+
+def test_decoder_dropout_stream_semantics():
+    """eval() never drops; train() draws a new mask every step (offset advances), the same (seed, step) reproduces the
+    same output bit for bit, and a large p visibly changes the result."""
+    from oracle import hh_oracle as O
+    from oracle import golden_cases as gc
+    from helping_hand_for_egocentric_videos_b200.model import tfm_decoder as D
+    c = gc.CASES["dec_tiny_traj"]["cfg"]
+    sd = O.synth_state_dict(O.decoder_param_shapes(c["C"], c["Q"], c["n"], c["T"], c["F"], c["ncls"] + 1, layers=c["layers"],
+                                                   ffn=c["ffn"], pred_traj=c["pred_traj"]), 5)
+    tr = D.Cross_Attention(d_model=c["C"], nhead=c["heads"], num_decoder_layers=c["layers"], dim_feedforward=c["ffn"],
+                           dropout=0.3, normalize_before=True, return_intermediate_dec=True)
+    dec = D.ObjDecoder(transformer=tr, num_classes=c["ncls"], num_queries=c["Q"], aux_loss=True, pred_traj=c["pred_traj"],
+                       feature_dim=c["F"], num_frames=c["T"], patches_per_frame=c["n"])
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.cuda()
+    x = torch.randn(2, c["T"], c["n"], c["F"], generator=torch.Generator().manual_seed(6)).cuda()
+    with torch.no_grad():
+        dec.eval()
+        e1 = dec(x)[1].clone()
+        e2 = dec(x)[1].clone()
+        assert torch.equal(e1, e2) and dec.last_dropout is None
+        dec.train()
+        dec.dropout_seed, dec._drop_step = 99, 0
+        t1 = dec(x)[1].clone()
+        assert dec.last_dropout == {"p": 0.3, "seed": 99, "offset": 0}
+        t2 = dec(x)[1].clone()
+        assert dec.last_dropout["offset"] == 1
+        dec._drop_step = 0
+        t3 = dec(x)[1].clone()
+    assert torch.equal(t1, t3)
+    assert not torch.equal(t1, t2)
+    assert (t1 - e1).abs().max().item() > 1e-2
