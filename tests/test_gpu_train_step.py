@@ -34,7 +34,11 @@ def _inputs(B, T, img, R, V, g):
                 noun_feats=noun_feats, inds=inds)
 
 
-def test_train_step_matches_oracle_autograd():
+@pytest.mark.parametrize("train_mode", [False, True])
+def test_train_step_matches_oracle_autograd(train_mode):
+    """train_mode: the decoder in train() as in run/train.py (dropout 0.1 at six sites per layer), the oracle graph with
+    the same masks; otherwise eval() arithmetic."""
+    drop = {"p": 0.1, "seed": 0xBEEF1234, "offset": 0} if train_mode else None
     from helping_hand_for_egocentric_videos_b200.model import LaviLa, box_utils, loss, metric, tfm_decoder as D
     B, T, img, R, V, Q = 4, 4, 56, 5, 40, 13
     enc = dict(img=img, patch=14, D=128, L=2, H=2, T=T, text_width=768, text_heads=12, text_layers=1, vocab=128)
@@ -50,7 +54,7 @@ def test_train_step_matches_oracle_autograd():
     with torch.no_grad():
         bo = O.clip_forward(inp["video"], inp["tokens"], bsd, heads=2, text_heads=12)
     grid = bo["image_feature_map"][:, 1:].unflatten(1, (T, 16))
-    out, hs, _, _ = O.decoder_forward(grid, ref, heads=2, pred_traj=True)
+    out, hs, _, _ = O.decoder_forward(grid, ref, heads=2, pred_traj=True, dropout=drop)
     txt = O.txt_proj(bo["text_feature_map"][torch.arange(B * R), eot], ref)
     vid = O.obj_proj(hs[-1], ref)[:, -1]
     nce, _ = O.egonce_loss(O.sim_matrix(txt, vid), O.sim_matrix(inp["verb"], inp["verb"]),
@@ -77,6 +81,9 @@ def test_train_step_matches_oracle_autograd():
                          num_frames=T, patches_per_frame=16)
     model.load_state_dict(dsd, strict=True)
     model = model.cuda().eval()
+    if train_mode:
+        model.train()
+        model.dropout_seed, model._drop_step = drop["seed"], drop["offset"]
     crit = box_utils.SetCriterion(22047, matcher=box_utils.build_matcher(None), weight_dict=wd, eos_coef=0.1,
                                   losses=["boxes", "cardinality"]).cuda()
     dev = {k: v.cuda() for k, v in inp.items()}
@@ -95,6 +102,7 @@ def test_train_step_matches_oracle_autograd():
     word2 = loss.WordContrastiveLoss()(model.txt_proj(dev["noun_feats"]), emb2[:, :-1].contiguous(), dev["inds"])
     total2 = nce2 + lh2 + lo2 + 0.5 * word2
     total2.backward()
+    assert model.last_dropout == drop
 
     for a, b, nm in ((nce2, nce, "nce"), (lh2, lh, "hand"), (lo2, lo_, "obj"), (word2, word, "word")):
         assert abs(a.item() - b.item()) <= 2e-2 * max(1.0, abs(b.item())), (nm, a.item(), b.item())

@@ -1,6 +1,7 @@
 """BASELINE config c4 on one GPU's share (64 clips x 4 frames, nq=12, 5 captions per clip): time of the frozen-backbone
 forward, the decoder training forward, the three losses and the backward, with CUDA events.  Not a bench.py line (c4 is
-a parity configuration); used to find the slow kernels of the training path.   python tools/bench_train_step.py [B]"""
+a parity configuration); used to find the slow kernels of the training path.
+  python tools/bench_train_step.py [B] [eval|train]      train (default): decoder in train() mode, dropout 0.1"""
 import sys
 import time
 
@@ -25,6 +26,9 @@ def main():
                          num_frames=T, patches_per_frame=256)
     synthetic.randomize_(model, 1)
     model = model.cuda().eval()
+    if len(sys.argv) <= 2 or sys.argv[2] != "eval":
+        model.train()        # run/train.py trains the decoder in train() mode: dropout at six sites per layer
+    print("decoder mode:", "train (dropout %.2f)" % tr.dropout_p if model.training else "eval", flush=True)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
     crit = box_utils.SetCriterion(22047, matcher=box_utils.build_matcher(None), eos_coef=0.1, losses=["boxes", "cardinality"],
                                   weight_dict={"loss_bbox_hand_boxes": 5, "loss_bbox_obj_boxes": 5,
