@@ -2,7 +2,8 @@
 // projection, the 6 layers' K/V projections, the class head) run on the tcgen05 GEMM; what is left operates on the
 // Q <= 16 learned queries per clip and is latency-, not FLOP-bound.  Everything here is fp32.
 //
-//   linear_f32          small-M nn.Linear (+ query_pos add on the input, bias, ReLU/sigmoid, residual)
+//   linear_f32          small-M nn.Linear (+ query_pos add on the input, bias, ReLU/sigmoid, residual); fp32 operands on
+//                       the tensor cores as error-compensated TF32 (3 MMAs per product, fp32-level accuracy)
 //   self_attn_queries   nn.MultiheadAttention core over the Q queries (tfm_decoder.py:433)
 //   cross_attn          query -> patch-token attention core (tfm_decoder.py:438-441), split over keys (flash-decode
 //                       style) with an exact merge; the head-averaged attention map the reference computes and
@@ -20,11 +21,16 @@ constexpr int HD = 64;
 // ------------------------------------------------------------------------------------------ linear_f32
 constexpr int LBM = 32, LBN = 64, LBK = 32;
 
+// Tensor-core inner product (3xTF32, fp32-level accuracy): 8 warps = 2 row blocks of 16 x 4 column blocks of 16.
+constexpr int LSA = LBK + 4;   // smem row stride: fragment loads (rows g, columns t) hit 32 distinct banks
+
 __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
-  __shared__ float As[LBM][LBK + 1];
-  __shared__ float Ws[LBN][LBK + 1];
+  __shared__ __align__(16) float As[LBM][LSA];
+  __shared__ __align__(16) float Ws[LBN][LSA];
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
   const int r0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
   float acc[2][4];
 #pragma unroll
@@ -47,7 +53,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
           v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
       }
-      As[r][kk] = v.x; As[r][kk + 1] = v.y; As[r][kk + 2] = v.z; As[r][kk + 3] = v.w;
+      *reinterpret_cast<float4*>(&As[r][kk]) = v;
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {  // W tile: 64 n x 32 k
@@ -55,30 +61,34 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
       const int nn = idx >> 3, kk = (idx & 7) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n0 + nn < a.N) v = *reinterpret_cast<const float4*>(a.W + static_cast<size_t>(n0 + nn) * a.K + k0 + kk);
-      Ws[nn][kk] = v.x; Ws[nn][kk + 1] = v.y; Ws[nn][kk + 2] = v.z; Ws[nn][kk + 3] = v.w;
+      *reinterpret_cast<float4*>(&Ws[nn][kk]) = v;
     }
     __syncthreads();
+    // the tensor core truncates when it accumulates: chain only this tile's 4 k-steps there and add the tile's
+    // partial to the running sum with a rounded fp32 add (keeps the result within ~5e-7 of an fp32 FMA chain)
+    float part[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-    for (int k = 0; k < LBK; ++k) {
-      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k];
+    for (int ks = 0; ks < LBK / 8; ++ks) {
+      const float af[4] = {As[wm * 16 + g][ks * 8 + t], As[wm * 16 + g + 8][ks * 8 + t], As[wm * 16 + g][ks * 8 + t + 4],
+                           As[wm * 16 + g + 8][ks * 8 + t + 4]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float w = Ws[tx + 16 * j][k];
-        acc[0][j] += a0 * w;
-        acc[1][j] += a1 * w;
-      }
+      for (int j = 0; j < 2; ++j)
+        mma_3xtf32(part[j], af, Ws[wn * 16 + j * 8 + g][ks * 8 + t], Ws[wn * 16 + j * 8 + g][ks * 8 + t + 4]);
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] += part[j][e];
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int row = r0 + ty * 2 + i;
-    if (row >= a.R) continue;
+  for (int j = 0; j < 2; ++j) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tx + 16 * j;
-      if (col >= a.N) continue;
-      float v = acc[i][j] + (a.bias ? a.bias[col] : 0.f);
+    for (int e = 0; e < 4; ++e) {
+      const int row = r0 + wm * 16 + g + (e >> 1) * 8;
+      const int col = n0 + wn * 16 + j * 8 + 2 * t + (e & 1);
+      if (row >= a.R || col >= a.N) continue;
+      float v = acc[j][e] + (a.bias ? a.bias[col] : 0.f);
       if (a.act == 1) v = fmaxf(v, 0.f);
       else if (a.act == 2) v = 1.f / (1.f + __expf(-v));
       if (a.drop.thr) v *= drop_mult(a.drop, a.drop_site, static_cast<uint64_t>(row) * a.N + col);

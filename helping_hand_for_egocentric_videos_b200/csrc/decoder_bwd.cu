@@ -1,5 +1,6 @@
 // Backward primitives of the object-aware decoder ("decoder / heads backward").
-// The query side (Q <= 16 rows per clip) stays fp32 SIMT like its forward; the memory side (B*S patch tokens) reuses
+// The query side (Q <= 16 rows per clip) keeps fp32 operands like its forward (linears as error-compensated TF32 on the
+// tensor cores, the rest SIMT); the memory side (B*S patch tokens) reuses
 // the tcgen05 GEMM for its data- and weight-gradient contractions (engine_bwd.cu) and needs from here only the
 // cross-attention backward, LayerNorm backward, column sums and transposes.
 //
@@ -26,11 +27,15 @@ __device__ __forceinline__ float act_grad(float dy, float y, int act) {
 
 // ------------------------------------------------------------------------------------------ linear backward
 // dX[r, k] = beta * dX[r, k] + sum_n g[r, n] * W[n, k],  g = act'(dY, Y)
+// Inner products on the tensor cores as error-compensated TF32 (mma_3xtf32: fp32-level accuracy); 8 warps = 2 row
+// blocks of 16 x 4 column blocks of 16; smem strides chosen so that fragment loads are bank-conflict free.
 __global__ void __launch_bounds__(256) linear_dgrad_kernel(const LinBwdArgs a) {
-  __shared__ float Gs[32][33];
-  __shared__ float Ws[32][65];
+  __shared__ float Gs[32][36];   // [r][n]
+  __shared__ float Ws[32][72];   // [n][k]
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
   const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   for (int n0 = 0; n0 < a.N; n0 += 32) {
@@ -49,38 +54,42 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const LinBwdArgs a) {
       Ws[n][k] = (n0 + n < a.N && k0 + k < a.K) ? a.W[static_cast<size_t>(n0 + n) * a.K + k0 + k] : 0.f;
     }
     __syncthreads();
+    float part[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // per-tile partial, see linear_f32_kernel
 #pragma unroll
-    for (int n = 0; n < 32; ++n) {
-      const float g0 = Gs[ty * 2][n], g1 = Gs[ty * 2 + 1][n];
+    for (int ks = 0; ks < 4; ++ks) {   // A = G (rows r, reduction n), B[n][k] = W
+      const float af[4] = {Gs[wm * 16 + g][ks * 8 + t], Gs[wm * 16 + g + 8][ks * 8 + t], Gs[wm * 16 + g][ks * 8 + t + 4],
+                           Gs[wm * 16 + g + 8][ks * 8 + t + 4]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float w = Ws[n][tx + 16 * j];
-        acc[0][j] += g0 * w;
-        acc[1][j] += g1 * w;
-      }
+      for (int j = 0; j < 2; ++j)
+        mma_3xtf32(part[j], af, Ws[ks * 8 + t][wn * 16 + j * 8 + g], Ws[ks * 8 + t + 4][wn * 16 + j * 8 + g]);
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] += part[j][e];
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int row = r0 + ty * 2 + i;
-    if (row >= a.R) continue;
+  for (int j = 0; j < 2; ++j) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = k0 + tx + 16 * j;
-      if (col >= a.K) continue;
+    for (int e = 0; e < 4; ++e) {
+      const int row = r0 + wm * 16 + g + (e >> 1) * 8;
+      const int col = k0 + wn * 16 + j * 8 + 2 * t + (e & 1);
+      if (row >= a.R || col >= a.K) continue;
       float* d = a.dX + static_cast<size_t>(row) * a.lddx + col;
-      *d = (a.beta != 0.f ? a.beta * *d : 0.f) + acc[i][j];
+      *d = (a.beta != 0.f ? a.beta * *d : 0.f) + acc[j][e];
     }
   }
 }
 
 // dW[n, k] = beta * dW[n, k] + scale * sum_r g[r, n] * x[r, k],  x = relu?(X + x_add[r % mod]);  db[n] likewise
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
-  __shared__ float Gs[32][33];   // [r][n]
-  __shared__ float Xs[32][65];   // [r][k]
+  __shared__ float Gs[32][40];   // [r][n]
+  __shared__ float Xs[32][72];   // [r][k]
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float bsum = 0.f;  // threads 0..31 of the k-tile-0 CTAs own one bias entry
@@ -110,31 +119,33 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const LinBwdArgs a) {
       Xs[r][k] = v;
     }
     __syncthreads();
+    float part[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // per-tile partial, see linear_f32_kernel
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const float g0 = Gs[r][ty * 2], g1 = Gs[r][ty * 2 + 1];
+    for (int ks = 0; ks < 4; ++ks) {   // A[n][r] = G^T (rows n, reduction r), B[r][k] = X
+      const float af[4] = {Gs[ks * 8 + t][wm * 16 + g], Gs[ks * 8 + t][wm * 16 + g + 8], Gs[ks * 8 + t + 4][wm * 16 + g],
+                           Gs[ks * 8 + t + 4][wm * 16 + g + 8]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = Xs[r][tx + 16 * j];
-        acc[0][j] += g0 * x;
-        acc[1][j] += g1 * x;
-      }
+      for (int j = 0; j < 2; ++j)
+        mma_3xtf32(part[j], af, Xs[ks * 8 + t][wn * 16 + j * 8 + g], Xs[ks * 8 + t + 4][wn * 16 + j * 8 + g]);
     }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] += part[j][e];
     if (a.db && blockIdx.x == 0 && tid < 32)
       for (int r = 0; r < 32; ++r) bsum += Gs[r][tid];
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int n = n0 + ty * 2 + i;
-    if (n >= a.N) continue;
+  for (int j = 0; j < 2; ++j) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = k0 + tx + 16 * j;
-      if (k >= a.K) continue;
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + wm * 16 + g + (e >> 1) * 8;
+      const int k = k0 + wn * 16 + j * 8 + 2 * t + (e & 1);
+      if (n >= a.N || k >= a.K) continue;
       float* d = a.dW + static_cast<size_t>(n) * a.ldw + k;
-      if (gridDim.z > 1) atomicAdd(d, a.scale * acc[i][j]);
-      else *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * acc[i][j];
+      if (gridDim.z > 1) atomicAdd(d, a.scale * acc[j][e]);
+      else *d = (a.beta != 0.f ? a.beta * *d : 0.f) + a.scale * acc[j][e];
     }
   }
   if (a.db && blockIdx.x == 0 && tid < 32 && n0 + tid < a.N) {
