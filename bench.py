@@ -129,7 +129,7 @@ def cpu_forward_clips(vsd, dsd, frames, nclips, threads):
     return time.perf_counter() - t0
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     """--impl reference: the reference's algorithm (oracle port: the reference itself is Python that needs
     /root/reference, which does not exist on the GPU box) on all host cores; bounded sample of 4 clips per step."""
     if rank != 0:
@@ -154,7 +154,7 @@ def run_reference(args, rank):
                              "sample": "%d clip(s) per step, %d steps, oracle/hh_oracle.py fp32 torch CPU" % (sample, steps)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -171,8 +171,19 @@ def main():
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries exactly one JSON line: while the benchmark runs, file descriptor 1 points at stderr, so that
+    # anything a C library prints there (NCCL's "NCCL version ..." banner when the box sets NCCL_DEBUG) cannot end up in
+    # front of it; the descriptor is restored for the final print
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import torch.distributed as dist
@@ -363,7 +374,7 @@ def main():
         line["cpu_baseline"] = {"value": 4.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "4 clips (same L/14, %d-frame, nq=%d path) through oracle/hh_oracle.py, fp32 "
                                           "torch CPU, %.1f s" % (T, nq, dt)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
