@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < a.K; k0 += LBK) {
+  // software pipeline: the next K tile's global loads are issued before this tile's MMAs and land in registers while
+  // they run (few CTAs per SM here: the load latency is otherwise fully exposed every iteration)
+  float4 ra, rw[2];
+  auto load_tiles = [&](int k0) {
     {  // A tile: 32 rows x 32 k, one float4 per thread
       const int r = tid >> 3, kk = (tid & 7) * 4;
       const int row = r0 + r;
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
           v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
       }
-      *reinterpret_cast<float4*>(&As[r][kk]) = v;
+      ra = v;
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {  // W tile: 64 n x 32 k
@@ -61,9 +64,19 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinArgs a) {
       const int nn = idx >> 3, kk = (idx & 7) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n0 + nn < a.N) v = *reinterpret_cast<const float4*>(a.W + static_cast<size_t>(n0 + nn) * a.K + k0 + kk);
-      *reinterpret_cast<float4*>(&Ws[nn][kk]) = v;
+      rw[it] = v;
+    }
+  };
+  load_tiles(0);
+  for (int k0 = 0; k0 < a.K; k0 += LBK) {
+    *reinterpret_cast<float4*>(&As[tid >> 3][(tid & 7) * 4]) = ra;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = tid + it * 256;
+      *reinterpret_cast<float4*>(&Ws[idx >> 3][(idx & 7) * 4]) = rw[it];
     }
     __syncthreads();
+    if (k0 + LBK < a.K) load_tiles(k0 + LBK);
     // the tensor core truncates when it accumulates: chain only this tile's 4 k-steps there and add the tile's
     // partial to the running sum with a rounded fp32 add (keeps the result within ~5e-7 of an fp32 FMA chain)
     float part[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
