@@ -69,6 +69,14 @@ __device__ __forceinline__ void trace_ev(const TcArgs& p, int role, int it, int 
   }
 }
 
+// tasks are walked from the last (clip, frame, head): those q/k/v rows were written last by the QKV GEMM and are still
+// in L2, and the projection GEMM that follows reads the rows this kernel writes last (the first clips) first
+#ifdef HH_FORWARD_WALK
+#define HH_TASK(t) (t)
+#else
+#define HH_TASK(t) (ntasks - 1 - (t))
+#endif
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -122,7 +130,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
+        const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
         mbar_wait(&ex->empty[st], ph ^ 1u);
         trace_ev(p, 0, it, 0);
         uint8_t* base = smem + st * STAGE_BYTES;
@@ -193,7 +201,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
+      const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
       mbar_wait(&ex->full[st], ph);
       if (ww == 0 && lane == 0) trace_ev(p, 2, it, 0);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
@@ -374,7 +382,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const int st = u & 1;
       const uint32_t ph = (u >> 1) & 1;
       const uint32_t tp = u & 1;
-      const int h = task % p.H, f = (task / p.H) % p.T, b = task / (p.H * p.T);
+      const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
       mbar_wait(&ex->full[st], ph);        // TMA-written cls_v visible to this thread
       mbar_wait(&ex->scls_full[st], ph);

@@ -44,7 +44,12 @@ attn_time_v2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float*
   const int hgroups = (H + TW - 1) / TW;
   const int chunk = blockIdx.x % nchunks;
   const int hg = (blockIdx.x / nchunks) % hgroups;
+  // last clips first: their q/k/v rows were written last by the QKV GEMM and are still in L2 (see rows.cu)
+#ifdef HH_FORWARD_WALK
   const int b = blockIdx.x / (nchunks * hgroups);
+#else
+  const int b = static_cast<int>(gridDim.x) / (nchunks * hgroups) - 1 - static_cast<int>(blockIdx.x) / (nchunks * hgroups);
+#endif
   const int h = hg * TW + warp;
   if (h >= H) return;  // whole warp; no block-level barriers below
   const size_t ld = static_cast<size_t>(3) * D;
