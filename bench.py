@@ -148,8 +148,10 @@ def run_reference(args, rank, emit):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TimeSformer-L/14 + tfm_decoder nq=%d, %d frames 224^2, EgoMCQ-style scoring" % (
-                args.nq, args.frames), "clips_per_step": sample},
+            "config": {"workload": "TimeSformer-L/14 + tfm_decoder nq=%d, %d frames 224^2, batch %d clips/GPU, "
+                                   "EgoMCQ-style scoring (BASELINE.json configs[2])" % (args.nq, args.frames, args.batch),
+                       "frames": args.frames, "nq": args.nq, "clips_per_step": sample,
+                       "sample": "bounded sample of the workload: %d clips per step on the host cores" % sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d clip(s) per step, %d steps, oracle/hh_oracle.py fp32 torch CPU" % (sample, steps)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -337,15 +339,16 @@ def main():
             per_class[k]["tflops"] = gemm_flops[k] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12
     # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture at these very shapes
     # (profiles/r1_gemm_traffic.json), averaged over the launches of one step like `achieved`.
-    traffic = None
+    traffic, traffic_detail = None, None
     tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
     if os.path.isfile(tpath) and B == 64 and T == 16:
         with open(tpath) as f:
             tk = json.load(f)["kernels"]
         per_step = {"qkv": 48, "proj": 48, "fc1": 24, "fc2": 24}
-        traffic = {"avg_dram_bytes_per_launch": sum(tk[k]["dram_bytes_per_launch"] * c for k, c in per_step.items()) / 144,
-                   "avg_algorithmic_bytes_per_launch": sum(tk[k]["algorithmic_bytes"] * c for k, c in per_step.items()) / 144,
-                   "source": "profiles/r1_gemm_ncu_full.md"}
+        traffic = sum(tk[k]["dram_bytes_per_launch"] * c for k, c in per_step.items()) / 144   # bytes per launch
+        traffic_detail = {"avg_dram_bytes_per_launch": traffic,
+                          "avg_algorithmic_bytes_per_launch": sum(tk[k]["algorithmic_bytes"] * c for k, c in per_step.items()) / 144,
+                          "source": "profiles/r1_gemm_ncu_full.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
     path_tflops = value / world * flops_clip / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -361,7 +364,8 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05, encoder qkv/proj/fc1/fc2 launches)",
                      "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["sustained"], "peak_source": peaks["source"] + " sustained bf16",
-                     "share_of_step": g_ms / args.steps / ms_step if ms_step > 0 else None, "traffic": traffic},
+                     "share_of_step": g_ms / args.steps / ms_step if ms_step > 0 else None, "traffic": traffic,
+                     "traffic_detail": traffic_detail},
         "clocks": clocks, "gpu_launches": launches_step * args.steps,
     }
     if e2e:
