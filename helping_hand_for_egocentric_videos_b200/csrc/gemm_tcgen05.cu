@@ -30,13 +30,16 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int STAGE_LD = 33;  // per-warp transpose buffer: 32 rows x 33 words
 
-template <int BLOCK_N, bool TWOSM = false>
+// DEEP_EPI (the QuickGELU epilogue of the 2-SM path): a 4-slot store ring per epilogue warp and one operand stage fewer
+// (same shared-memory total).  A/B on one box: fc1 43.3 -> 41.8 ms per step; the plain-bias GEMMs prefer the sixth
+// operand stage (qkv 61.7 -> 62.6 ms with the deep ring), so they keep 2 slots.
+template <int BLOCK_N, bool TWOSM = false, bool DEEP_EPI = false>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256 && !TWOSM) ? 4 : 6;
-  static constexpr int EPI_SLOTS = 2;                              // per-warp ring of 32-row x 128-byte store slots
+  static constexpr int STAGES = (BLOCK_N == 256 && !TWOSM) ? 4 : ((TWOSM && DEEP_EPI) ? 5 : 6);
+  static constexpr int EPI_SLOTS = (TWOSM && DEEP_EPI) ? 4 : 2;      // per-warp ring of 32-row x 128-byte store slots
   static constexpr int EPI_BYTES = 4 * EPI_SLOTS * 4096;            // (>= the 4 x 32 x 33 words of the direct path)
   static constexpr int BIAS_BYTES = BLOCK_N * 4;
   static constexpr int BAR_BYTES = 256;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, const GemmArgs p) {
   static_assert(!TWOSM || (CLUSTER && TMA_STORE), "the 2-SM MMA path runs as a CTA pair");
-  using C = Cfg<BLOCK_N, TWOSM>;
+  using C = Cfg<BLOCK_N, TWOSM, EPI == EPI_BIAS_QGELU_BF16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -441,7 +444,7 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
 
 template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER, bool TWOSM = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& args, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, TWOSM>;
+  using C = Cfg<BLOCK_N, TWOSM, EPI == EPI_BIAS_QGELU_BF16>;
   static bool configured = false;
   auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE, CLUSTER, TWOSM>;
   if (!configured) {
