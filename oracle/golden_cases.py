@@ -32,6 +32,12 @@ CASES = {
     "dec_c0": dict(kind="decoder", seed=23, B=2, G=2,
                    cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=5, n=196, T=4, F=768, ncls=22047, pred_traj=True),
                    logit_stride=37),
+    # the decoder in train() mode: dropout at six sites per layer (nn.Dropout x4, both nn.MultiheadAttention modules'
+    # attention probabilities) with the masks of hh_oracle.philox_keep injected into the reference through
+    # torch.nn.functional.dropout; outputs and the reference's autograd gradients of a fixed linear functional
+    "dec_train_dropout": dict(kind="decoder_train", seed=24, B=2, G=3,
+                              cfg=dict(C=128, heads=2, layers=2, ffn=256, Q=5, n=16, T=3, F=128, ncls=30, pred_traj=True),
+                              dropout=dict(p=0.1, seed=0x5EED0123456789, offset=7)),
     "boxes": dict(kind="boxes", seed=31, N=40, M=7),
     "score": dict(kind="score", seed=41, Na=6, Nb=10, d=256, G=12),
     # training-side rows a17-a19: matcher indices, EgoNCE (multi-positive, single-positive, noun-only), word loss,
@@ -73,7 +79,7 @@ def make_inputs(case):
         c = case["cfg"]
         video = torch.randn(case["B"], c["T"], 3, c["img"], c["img"], generator=g)
         return video, make_tokens(case["G"], c["vocab"], g)
-    if kind == "decoder":
+    if kind in ("decoder", "decoder_train"):
         c = case["cfg"]
         feats = torch.randn(case["B"], c["T"], c["n"], c["F"], generator=g)
         return feats, torch.randn(case["G"], 768, generator=g)
@@ -203,9 +209,42 @@ def subsample(case, res):
     return out
 
 
+def train_functional(case, forward, obj_proj, params):
+    """Shared by the reference run (oracle/make_golden.py) and the oracle run: outputs of the training-mode forward and
+    the gradients of a fixed random linear functional of (hs, all layers' boxes, obj_proj embeddings) w.r.t. every
+    parameter (strided subsample + L2 norm per tensor).  forward(feats) -> (out, hs); params: name -> leaf tensor."""
+    c = case["cfg"]
+    feats, _ = make_inputs(case)
+    g = torch.Generator().manual_seed(case["seed"] + 2000)
+    out, hs = forward(feats)
+    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+    emb = obj_proj(hs[-1])
+    loss = (hs * torch.randn(hs.shape, generator=g)).sum() + (boxes * torch.randn(boxes.shape, generator=g)).sum() + \
+        (emb * torch.randn(emb.shape, generator=g)).sum()
+    loss.backward()
+    res = {"hs": hs.detach().clone(), "boxes": boxes.detach().clone(), "embed": emb.detach().clone(),
+           "loss": loss.detach().clone()}
+    for k in sorted(params):
+        gr = params[k].grad
+        if gr is None:
+            gr = torch.zeros_like(params[k])
+        flat = gr.detach().flatten()
+        res["grad/" + k] = flat[::max(1, flat.numel() // 64)][:64].clone()
+        res["gnorm/" + k] = flat.norm().clone()
+    return res
+
+
 def run_oracle(case):
     """The restatement's answer for a case, in the same (subsampled) form as the fixture."""
     kind = case["kind"]
+    if kind == "decoder_train":
+        c = case["cfg"]
+        sd = {k: v.clone().requires_grad_(True) for k, v in decoder_state_dict(case).items()}
+
+        def fwd(feats):
+            out, hs, _, _ = O.decoder_forward(feats, sd, heads=c["heads"], pred_traj=c["pred_traj"], dropout=case["dropout"])
+            return out, hs
+        return train_functional(case, fwd, lambda h: O.obj_proj(h, sd), sd)
     if kind == "losses":
         def word(nouns, pred, inds):
             loss, cols = O.word_contrastive_loss(nouns, pred, inds)

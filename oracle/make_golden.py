@@ -56,6 +56,53 @@ def run_reference(case):
         return gc.run_losses(gc.make_inputs(case), ns.metric.sim_matrix,
                              lambda x, mv, mn, pad: nce(x, mv, mn, multi_pad_mask=pad, strict_mask=True), word,
                              lambda o, t, e: m(o, t, exclude_class=e), box)
+    if kind == "decoder_train":
+        # The UNMODIFIED reference decoder in train() mode.  Only torch's dropout primitive is swapped: every call of
+        # torch.nn.functional.dropout (nn.Dropout.forward and the attention-weight dropout inside
+        # F.multi_head_attention_forward both resolve to it) draws its mask from hh_oracle.philox_keep, site = call
+        # order within the forward: per layer [self-attn probs, dropout1, cross-attn probs, dropout2, FFN inner, dropout3]
+        # (model/tfm_decoder.py:431-459).  The reference's tensors are sequence-first [Q, B, C]; the mask index is
+        # defined batch-first (b, q, c), hence the transpose for those sites.
+        import torch.nn.functional as F
+        from oracle import hh_oracle as O
+        c, dr = case["cfg"], case["dropout"]
+        dec = ref_import.build_reference_decoder(
+            ns, num_queries=c["Q"], feature_dim=c["F"], num_frames=c["T"], patches_per_frame=c["n"],
+            pred_traj=c["pred_traj"], num_classes=c["ncls"], d_model=c["C"], nhead=c["heads"],
+            dec_layers=c["layers"], ffn=c["ffn"])
+        dec.load_state_dict(gc.decoder_state_dict(case), strict=True)
+        dec.train()
+        assert dec.transformer.decoder.layers[0].dropout1.p == dr["p"]        # Cross_Attention default dropout=0.1
+        calls = {"k": 0}
+        real_dropout = F.dropout
+
+        def philox_dropout(input, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return input
+            k = calls["k"]
+            calls["k"] += 1
+            layer, kind_ = divmod(k, 6)
+            site = layer * 8 + kind_
+            assert abs(p - dr["p"]) < 1e-12
+            m = O.philox_keep(dr["seed"], dr["offset"], site, input.numel(), p)
+            if kind_ in (0, 2):                                   # attention probabilities [B*heads, Lq, Lk]
+                m = m.view(input.shape)
+            else:                                                 # [Q, B, C] sequence-first
+                qn, bn, cn = input.shape
+                m = m.view(bn, qn, cn).transpose(0, 1)
+            return input * m
+        F.dropout = philox_dropout
+        try:
+            params = dict(dec.named_parameters())
+
+            def fwd(feats):
+                out, hs, _, _ = dec(feats)
+                return out, hs
+            res = gc.train_functional(case, fwd, dec.obj_proj, params)
+        finally:
+            F.dropout = real_dropout
+        assert calls["k"] == 6 * c["layers"], calls
+        return res
     with torch.no_grad():
         if kind == "encoder":
             c = case["cfg"]
