@@ -81,12 +81,16 @@ def all_gather_packed(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return outs
 
 
+def sharded_sim_operands(text_local: torch.Tensor, video_local: torch.Tensor):
+    """Host logic of the sharded similarity: this rank's text rows stay local, the video embeddings of all ranks are
+    gathered once (rank order).  Returns (text_local, video_all)."""
+    (video_all,) = all_gather_packed([video_local])
+    return text_local, video_all
+
+
 def sharded_sim_matrix(text_local: torch.Tensor, video_local: torch.Tensor) -> torch.Tensor:
     """Rows of sim_matrix(text_all, video_all) owned by this rank: gather the video embeddings once, score the local
-    text rows against all of them (EPIC-MIR over 8 GPUs, BASELINE config 4)."""
-    (video_all,) = all_gather_packed([video_local])
-    if text_local.is_cuda:
-        return ops.sim_matrix(text_local, video_all)
-    a = text_local / text_local.norm(dim=-1, keepdim=True).clamp_min(1e-8)
-    b = video_all / video_all.norm(dim=-1, keepdim=True).clamp_min(1e-8)
-    return a @ b.t()
+    text rows against all of them on the device (EPIC-MIR over 8 GPUs, BASELINE config 4).  CUDA tensors only -- the
+    scoring kernel has no CPU fallback (ops.sim_matrix raises)."""
+    a, b = sharded_sim_operands(text_local, video_local)
+    return ops.sim_matrix(a, b)
