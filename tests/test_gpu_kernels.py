@@ -242,3 +242,10 @@ def test_hungarian_indices_from_gpu_cost_match_reference_cost():
         mine = linear_sum_assignment(ops.box_match_cost(p.cuda(), t.cuda()).cpu().numpy())
         ref = linear_sum_assignment(O.matcher_cost(p, t).numpy())
         assert (mine[0] == ref[0]).all() and (mine[1] == ref[1]).all()
+
+
+def test_sharded_sim_matrix_single_process():
+    """World size 1: the sharded similarity is the plain device scoring kernel (multi-rank host logic: gloo tests)."""
+    from helping_hand_for_egocentric_videos_b200 import parallel
+    a, b = _rand(9, 256, seed=70), _rand(14, 256, seed=71)
+    _close(parallel.sharded_sim_matrix(a, b), O.sim_matrix(a, b), 1e-5, 1e-6, "sharded sim")
