@@ -23,6 +23,9 @@ CASES = {
     # BASELINE config c0 geometry (TimeSformer-B/16, 4 frames, batch 2); outputs subsampled to stay small
     "enc_c0": dict(kind="encoder", seed=13, B=2, G=2,
                    cfg=dict(img=224, patch=16, D=768, L=12, H=12, T=4, **_TXT), stride=(29, 7)),
+    # BASELINE c1 / c2 encoder geometry (TimeSformer-L/14: D=1024, 24 layers, 16 heads, 256 patches), 4 frames, 1 clip
+    "enc_l14": dict(kind="encoder", seed=14, B=1, G=2,
+                    cfg=dict(img=224, patch=14, D=1024, L=24, H=16, T=4, **_TXT), stride=(41, 13)),
     "dec_tiny_traj": dict(kind="decoder", seed=21, B=2, G=3,
                           cfg=dict(C=128, heads=2, layers=2, ffn=256, Q=5, n=16, T=3, F=128, ncls=30, pred_traj=True)),
     "dec_tiny_notraj": dict(kind="decoder", seed=22, B=3, G=2,
