@@ -35,6 +35,11 @@ CASES = {
     "dec_c0": dict(kind="decoder", seed=23, B=2, G=2,
                    cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=5, n=196, T=4, F=768, ncls=22047, pred_traj=True),
                    logit_stride=37),
+    # BASELINE c2 decoder geometry (the headline configuration): nq = 12 -> Q = 13, 16 frames x 256 patches of 1024-d
+    # features, no trajectory head (run/test_epic.py:150-153), full class head
+    "dec_c2": dict(kind="decoder", seed=25, B=1, G=2,
+                   cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=13, n=256, T=16, F=1024, ncls=22047, pred_traj=False),
+                   logit_stride=37),
     # the decoder in train() mode: dropout at six sites per layer (nn.Dropout x4, both nn.MultiheadAttention modules'
     # attention probabilities) with the masks of hh_oracle.philox_keep injected into the reference through
     # torch.nn.functional.dropout; outputs and the reference's autograd gradients of a fixed linear functional
