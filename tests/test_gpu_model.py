@@ -53,7 +53,7 @@ def _build_decoder(case):
     return dec.cuda().eval(), sd
 
 
-@pytest.mark.parametrize("name", ["enc_tiny", "enc_tiny_d1", "enc_c0", "enc_l14"])
+@pytest.mark.parametrize("name", ["enc_tiny", "enc_tiny_d1", "enc_c0", "enc_l14", "txt_large"])
 def test_encoder_against_reference_golden(name):
     case = gc.CASES[name]
     ref = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
