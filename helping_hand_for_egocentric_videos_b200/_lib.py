@@ -50,6 +50,8 @@ SIGNATURES = {
     "hh_decoder_forward_train": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
     "hh_decoder_set_dropout": (_i, [_p, _f, C.c_uint64, C.c_uint32]),
     "hh_decoder_backward": (_i, [_p, _p, _p, _p, _p, _p]),
+    "hh_decoder_generation": (C.c_uint64, [_p]),
+    "hh_decoder_backward_checked": (_i, [_p, C.c_uint64, _p, _p, _p, _p, _p]),
     "hh_decoder_get_grad": (_i, [_p, C.c_char_p, _p, _i64, _p]),
     "hh_decoder_flops_per_clip": (C.c_double, [_p, _i]),
     "hh_decoder_last_launches": (_i, [_p]),
@@ -91,6 +93,10 @@ SIGNATURES = {
     "hh_box_pairwise": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
     "hh_box_match_cost": (_i, [_p, _p, _i, _i, _f, _f, _p, _p]),
     "hh_gemm_bf16": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "hh_gemm_stats_parts": (_i, [_i, _i]),
+    "hh_fold_layernorm_weight": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "hh_gemm_bf16_res_stats": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _p, _i, _i, _i, _p]),
+    "hh_gemm_bf16_ln": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _i, _i, _f, _i, _i, _i, _i, _p]),
     "hh_layernorm": (_i, [_p, _i, _p, _p, _f, _p, _p, _i, _i, _p]),
     "hh_f32_to_bf16": (_i, [_p, _p, _i64, _p]),
     "hh_attention": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

@@ -130,6 +130,18 @@ int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, co
   return dec->impl.backward(hs, boxes, d_hs, d_boxes, S(stream));
   HH_GUARD_END
 }
+uint64_t hh_decoder_generation(const hh_decoder* dec) { return dec ? dec->impl.generation : 0; }
+int hh_decoder_backward_checked(hh_decoder* dec, uint64_t generation, const float* hs, const float* boxes, const float* d_hs,
+                                const float* d_boxes, void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec) return fail(-1, "hh_decoder_backward_checked: null handle");
+  if (dec->impl.generation != generation)
+    return fail(-2, "hh_decoder_backward: the engine's saved activations belong to forward #" +
+                        std::to_string(dec->impl.generation) + ", not to forward #" + std::to_string(generation) +
+                        " (another forward ran in between; call backward before the next forward)");
+  return dec->impl.backward(hs, boxes, d_hs, d_boxes, S(stream));
+  HH_GUARD_END
+}
 int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream) {
   HH_GUARD_BEGIN
   if (!dec || !key || !out) return fail(-2, "hh_decoder_get_grad: null argument");
@@ -340,6 +352,31 @@ int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int 
                  const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream) {
   return gemm_bf16(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, out, ldc, bias, residual, ldr, M,
                    N, K, epilogue, S(stream));
+}
+int hh_gemm_stats_parts(int M, int N) { return gemm_stats_parts(M, N); }
+int hh_fold_layernorm_weight(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                             int scaled_rows, float scale, void* Wf, float* colsum, float* bias_f, void* stream) {
+  return fold_ln_weight(W, gamma, beta, bias, static_cast<bf16*>(Wf), colsum, bias_f, N, K, scaled_rows, scale, S(stream));
+}
+int hh_gemm_bf16_res_stats(const void* A, int lda, const void* W, int ldw, void* z16, int ldz, const float* bias,
+                           float* residual, int ldr, int writeback, float* stats, int M, int N, int K, void* stream) {
+  GemmFuse f;
+  f.stats_out = stats;
+  f.writeback = writeback;
+  return gemm_bf16_fused(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, z16, ldz, bias, residual, ldr, M,
+                         N, K, EPI_RES_STATS_BF16, f, S(stream));
+}
+int hh_gemm_bf16_ln(const void* A, int lda, const void* Wf, int ldw, void* out, int ldc, const float* bias_f,
+                    const float* colsum, const float* stats, int parts, int norm_dim, float eps, int M, int N, int K,
+                    int qgelu, void* stream) {
+  GemmFuse f;
+  f.colsum = colsum;
+  f.stats_in = stats;
+  f.stats_parts = parts;
+  f.norm_dim = norm_dim;
+  f.eps = eps;
+  return gemm_bf16_fused(static_cast<const bf16*>(A), lda, static_cast<const bf16*>(Wf), ldw, out, ldc, bias_f, nullptr, 0, M,
+                         N, K, qgelu ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_BF16, f, S(stream));
 }
 int hh_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, float* out_f32, void* out_bf16,
                  int M, int D, void* stream) {

@@ -88,7 +88,8 @@ constexpr int MAX_VEC = 8;
 __global__ void __launch_bounds__(256)
 assemble_ln_kernel(const float* __restrict__ tok, const float* __restrict__ cls, const float* __restrict__ pos,
                    const float* __restrict__ temporal, const float* __restrict__ w, const float* __restrict__ b,
-                   float eps, float* __restrict__ x, int B, int T, int n, int D) {
+                   float eps, float* __restrict__ x, int B, int T, int n, int D, bf16* __restrict__ z16,
+                   float* __restrict__ stats) {
   const int N = 1 + T * n;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,7 +146,24 @@ assemble_ln_kernel(const float* __restrict__ tok, const float* __restrict__ cls,
       y.z = v[j].z * rstd * ww.z + bb.z;
       y.w = v[j].w * rstd * ww.w + bb.w;
       *reinterpret_cast<float4*>(xr + c) = y;
+      v[j] = y;
     }
+  }
+  if (z16) {  // operands of the first folded-LayerNorm GEMM: bf16 copy of the row and its (sum, sum of squares)
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_VEC; ++j) {
+      if (j < nv) {
+        const int c = (j * 32 + lane) * 4;
+        s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        s2 += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        *reinterpret_cast<uint2*>(z16 + static_cast<size_t>(row) * D + c) =
+            make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + static_cast<size_t>(row) * 2) = make_float2(s1, s2);
   }
 }
 
@@ -185,11 +203,13 @@ int im2col_patches_u8(const uint8_t* frames, const float* mean, const float* std
 }
 
 int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, const float* temporal, const float* w,
-                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream) {
+                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream, bf16* z16,
+                       float* stats) {
   HH_REQUIRE(D % 128 == 0 && D <= 128 * MAX_VEC, "assemble_tokens_ln: D must be a multiple of 128, at most 1024");
+  HH_REQUIRE((z16 == nullptr) == (stats == nullptr), "assemble_tokens_ln: z16 and stats come together");
   const int rows = B * (1 + T * n);
   const int grid = (rows + 7) / 8;
-  assemble_ln_kernel<<<grid, 256, 0, stream>>>(tok, cls, pos, temporal, w, b, eps, x, B, T, n, D);
+  assemble_ln_kernel<<<grid, 256, 0, stream>>>(tok, cls, pos, temporal, w, b, eps, x, B, T, n, D, z16, stats);
   HH_CHECK_LAUNCH("assemble_ln_kernel");
   return 0;
 }

@@ -132,6 +132,7 @@ Encoder::Encoder(const hh_encoder_cfg& c) : cfg(c) {
     const int v = std::atoi(e);
     if (v > 0) max_chunk = v;
   }
+  if (const char* e = std::getenv("HH_LN_UNFUSED")) fused_ln = !(e[0] && e[0] != '0');
   grid = cfg.img_size / cfg.patch_size;
   n = grid * grid;
   N = 1 + cfg.num_frames * n;
@@ -186,17 +187,33 @@ int Encoder::pack(cudaStream_t s) {
     const std::string p = "blocks." + std::to_string(i) + ".";
     Layer& L = layers[i];
     const char* ats[2] = {"timeattn", "attn"};
+    const char* nms[2] = {"norm3", "norm1"};  // the LayerNorm in front of each attention's qkv (LaviLa.py:353,372)
     for (int a = 0; a < 2; ++a) {
       const std::string q = p + ats[a];
       RC(L.w_qkv[a].reserve(static_cast<size_t>(3) * D * D * 2));
-      RC(pack_weight_bf16(weights.get(q + ".qkv.weight"), static_cast<bf16*>(L.w_qkv[a].ptr), 3 * D, D, D, D, qscale, s));
       RC(L.b_qkv[a].reserve(static_cast<size_t>(3) * D * 4));
-      RC(scale_copy_f32(weights.get(q + ".qkv.bias"), static_cast<float*>(L.b_qkv[a].ptr), 3 * D, D, qscale, s));
+      if (fused_ln) {
+        RC(L.cs_qkv[a].reserve(static_cast<size_t>(3) * D * 4));
+        RC(fold_ln_weight(weights.get(q + ".qkv.weight"), weights.get(p + nms[a] + ".weight"), weights.get(p + nms[a] + ".bias"),
+                          weights.get(q + ".qkv.bias"), static_cast<bf16*>(L.w_qkv[a].ptr), static_cast<float*>(L.cs_qkv[a].ptr),
+                          static_cast<float*>(L.b_qkv[a].ptr), 3 * D, D, D, qscale, s));
+      } else {
+        RC(pack_weight_bf16(weights.get(q + ".qkv.weight"), static_cast<bf16*>(L.w_qkv[a].ptr), 3 * D, D, D, D, qscale, s));
+        RC(scale_copy_f32(weights.get(q + ".qkv.bias"), static_cast<float*>(L.b_qkv[a].ptr), 3 * D, D, qscale, s));
+      }
       RC(L.w_proj[a].reserve(static_cast<size_t>(D) * D * 2));
       RC(pack_weight_bf16(weights.get(q + ".proj.weight"), static_cast<bf16*>(L.w_proj[a].ptr), D, D, D, 0, 1.f, s));
     }
     RC(L.w_fc1.reserve(static_cast<size_t>(Hd) * D * 2));
-    RC(pack_weight_bf16(weights.get(p + "mlp.fc1.weight"), static_cast<bf16*>(L.w_fc1.ptr), Hd, D, D, 0, 1.f, s));
+    if (fused_ln) {  // norm2 -> fc1 (LaviLa.py:388)
+      RC(L.cs_fc1.reserve(static_cast<size_t>(Hd) * 4));
+      RC(L.b_fc1.reserve(static_cast<size_t>(Hd) * 4));
+      RC(fold_ln_weight(weights.get(p + "mlp.fc1.weight"), weights.get(p + "norm2.weight"), weights.get(p + "norm2.bias"),
+                        weights.get(p + "mlp.fc1.bias"), static_cast<bf16*>(L.w_fc1.ptr), static_cast<float*>(L.cs_fc1.ptr),
+                        static_cast<float*>(L.b_fc1.ptr), Hd, D, 0, 1.f, s));
+    } else {
+      RC(pack_weight_bf16(weights.get(p + "mlp.fc1.weight"), static_cast<bf16*>(L.w_fc1.ptr), Hd, D, D, 0, 1.f, s));
+    }
     RC(L.w_fc2.reserve(static_cast<size_t>(D) * Hd * 2));
     RC(pack_weight_bf16(weights.get(p + "mlp.fc2.weight"), static_cast<bf16*>(L.w_fc2.ptr), D, Hd, Hd, 0, 1.f, s));
   }
@@ -235,6 +252,7 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
   RC(ws_qkv.reserve(Mc * 3 * D * 2));
   RC(ws_h.reserve(Mc * Hd * 2));
   RC(ws_cls.reserve(attn_cls_workspace_bytes(chunk, T, n, H)));
+  if (fused_ln) RC(ws_stats.reserve(Mc * 2 * 4 * static_cast<size_t>(D / 128 > 1 ? D / 128 : 1)));
   bf16* patches = static_cast<bf16*>(ws_patches.ptr);
   float* tok = static_cast<float*>(ws_tok.ptr);
   float* x = static_cast<float*>(ws_x.ptr);
@@ -260,6 +278,10 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
     }
     PROF(K_GEMM_PATCH, gemm_bf16(patches, Kp, static_cast<const bf16*>(w_patch.ptr), Kp, tok, D, nullptr, nullptr, 0, P, D,
                                  Kp, EPI_BIAS_F32, s));
+    if (fused_ln) {
+      RC(run_blocks_fused(tok, Bc, nblocks, fmap + static_cast<size_t>(b0) * N * D, s));
+      continue;
+    }
     PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
                                      weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s));
     launches += 3;
@@ -319,6 +341,75 @@ int Encoder::run(const float* video, const uint8_t* frames, const float* mean, c
     RC(ln_fused(pending, pending2, false, "norm", 1e-6f, nullptr, fmap + static_cast<size_t>(b0) * N * D));
     launches += 1;
   }
+  return 0;
+}
+
+// Blocks with norm1 / norm2 / norm3 and the residual adds folded into the contractions (model/LaviLa.py:345-390).
+// Per layer, with x the fp32 stream, z a bf16 copy of the un-normalised GEMM input and (sum, sum^2) row statistics:
+//   qkv_t = Linear'(z, stats)                          norm3 folded into timeattn.qkv         (:353)
+//   z     = x + proj_t(attn_time(qkv_t)), stats        x itself untouched: 'frozen-in-time'   (:364)
+//   qkv_s = Linear'(z, stats)                          norm1 folded into attn.qkv             (:372)
+//   x, z  = x + proj_s(attn_space(qkv_s)), stats       fp32 sum written back in place         (:384)
+//   h     = QuickGELU(Linear'(z, stats))               norm2 folded into mlp.fc1              (:388)
+//   x, z  = x + fc2(h), stats                                                                 (:388)
+// x moves 26 bytes per element per layer (3 reads, 2 writes, 3 bf16 copies) instead of 36, in 8 launches instead of 11.
+int Encoder::run_blocks_fused(const float* tok, int Bc, int nblocks, float* fmap_out, cudaStream_t s) {
+  const int T = cfg.num_frames, D = cfg.embed_dim, H = cfg.num_heads, Hd = cfg.mlp_hidden;
+  const int M = Bc * N;
+  float* x = static_cast<float*>(ws_x.ptr);
+  bf16* z = static_cast<bf16*>(ws_dl.ptr);
+  bf16* a = static_cast<bf16*>(ws_a.ptr);
+  bf16* qkv = static_cast<bf16*>(ws_qkv.ptr);
+  bf16* h = static_cast<bf16*>(ws_h.ptr);
+  float* stats = static_cast<float*>(ws_stats.ptr);
+  float* cls_ws = static_cast<float*>(ws_cls.ptr);
+  PROF(K_EMBED, assemble_tokens_ln(tok, weights.get("cls_token"), weights.get("pos_embed"), weights.get("temporal_embed"),
+                                   weights.get("ln_pre.weight"), weights.get("ln_pre.bias"), 1e-5f, x, Bc, T, n, D, s, z, stats));
+  launches += 3;
+  int parts = 1;  // statistics partials per row currently in `stats`
+  const int parts_d = gemm_stats_parts(M, D);
+  auto consume = [&](const DevBuf& W, const DevBuf& bias, const DevBuf& cs, bf16* out, int Nout, int epi) {
+    GemmFuse f;
+    f.colsum = static_cast<const float*>(cs.ptr);
+    f.stats_in = stats;
+    f.stats_parts = parts;
+    f.norm_dim = D;
+    f.eps = 1e-6f;
+    return gemm_bf16_fused(z, D, static_cast<const bf16*>(W.ptr), D, out, Nout, static_cast<const float*>(bias.ptr), nullptr, 0,
+                           M, Nout, D, epi, f, s);
+  };
+  auto produce = [&](const bf16* A, int K, const DevBuf& W, const float* bias, bool writeback) {
+    GemmFuse f;
+    f.stats_out = stats;
+    f.writeback = writeback ? 1 : 0;
+    const int rc = gemm_bf16_fused(A, K, static_cast<const bf16*>(W.ptr), K, z, D, bias, x, D, M, D, K, EPI_RES_STATS_BF16, f, s);
+    parts = parts_d;
+    return rc;
+  };
+  for (int i = 0; i < nblocks; ++i) {
+    const std::string p = "blocks." + std::to_string(i) + ".";
+    const Layer& L = layers[i];
+    PROF(K_GEMM_QKV, consume(L.w_qkv[0], L.b_qkv[0], L.cs_qkv[0], qkv, 3 * D, EPI_LN_BIAS_BF16));
+    PROF(K_ATTN_TIME, attn_time(qkv, a, Bc, T, n, H, cls_ws, s));
+    PROF(K_GEMM_PROJ, produce(a, D, L.w_proj[0], weights.get(p + "timeattn.proj.bias"), false));
+    PROF(K_GEMM_QKV, consume(L.w_qkv[1], L.b_qkv[1], L.cs_qkv[1], qkv, 3 * D, EPI_LN_BIAS_BF16));
+    PROF(K_ATTN_SPACE, attn_space(qkv, a, Bc, T, n, H, cls_ws, s));
+    PROF(K_GEMM_PROJ, produce(a, D, L.w_proj[1], weights.get(p + "attn.proj.bias"), true));
+    PROF(K_GEMM_FC1, consume(L.w_fc1, L.b_fc1, L.cs_fc1, h, Hd, EPI_LN_BIAS_QGELU_BF16));
+    PROF(K_GEMM_FC2, produce(h, Hd, L.w_fc2, weights.get(p + "mlp.fc2.bias"), true));
+    launches += 8;
+  }
+  LnArgs ln{};
+  ln.x = x;
+  ln.ldx = D;
+  ln.w = weights.get("norm.weight");
+  ln.b = weights.get("norm.bias");
+  ln.eps = 1e-6f;
+  ln.out_f32 = fmap_out;
+  ln.M = M;
+  ln.D = D;
+  PROF(K_LN, layernorm_rows(ln, s));
+  launches += 1;
   return 0;
 }
 
@@ -468,6 +559,7 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
   HH_REQUIRE(T == cfg.num_frames, "decoder forward: T must equal num_frames (construct_3d_pos_embed, tfm_decoder.py:161-166)");
   if (weights.dirty) RC(pack(s));
   launches = 0;
+  ++generation;
   const int C = cfg.d_model, Lr = cfg.num_layers, F = cfg.feature_dim, Q = cfg.num_queries, Fd = cfg.dim_feedforward;
   const int n = cfg.patches_per_frame, S = T * n, heads = cfg.nhead, ncls = cfg.num_classes1;
   const int R = B * Q;

@@ -60,10 +60,15 @@ struct Encoder {
   struct Layer {
     DevBuf w_qkv[2], b_qkv[2], w_proj[2];  // [0] = timeattn, [1] = attn (space)
     DevBuf w_fc1, w_fc2;
+    // LayerNorm folded into the contraction (fused_ln): norm3 -> timeattn.qkv, norm1 -> attn.qkv, norm2 -> mlp.fc1
+    DevBuf cs_qkv[2], cs_fc1, b_fc1;       // column sums of the gamma-scaled bf16 weights; folded fc1 bias
   };
   std::vector<Layer> layers;
   DevBuf w_patch;
-  DevBuf ws_patches, ws_tok, ws_x, ws_dl, ws_dl2, ws_a, ws_qkv, ws_h, ws_cls;
+  DevBuf ws_patches, ws_tok, ws_x, ws_dl, ws_dl2, ws_a, ws_qkv, ws_h, ws_cls, ws_stats;
+  // true (default): norm1/2/3 and the residual adds live in the GEMM epilogues (model/LaviLa.py:353-388), the stand-alone
+  // LayerNorm kernel only runs for the final norm.  HH_LN_UNFUSED=1 keeps the round-1 sequence (A/B and differential tests).
+  bool fused_ln = true;
 
   explicit Encoder(const hh_encoder_cfg& c);
   static int validate(const hh_encoder_cfg& c);
@@ -76,6 +81,7 @@ struct Encoder {
  private:
   int run(const float* video, const uint8_t* frames, const float* mean, const float* stdv, int B, int nblocks, float* fmap,
           cudaStream_t s);
+  int run_blocks_fused(const float* tok, int Bc, int nblocks, float* fmap_out, cudaStream_t s);
 
  public:
 };
@@ -98,6 +104,8 @@ struct Decoder {
   };
   std::vector<LayerBufs> saved;
   int saved_B = 0, saved_T = 0;
+  // bumped by EVERY forward (the engine holds one activation set): backward() of an older forward must be refused
+  uint64_t generation = 0;
   // dropout of the training forward (hh_decoder_set_dropout): `next_drop` applies to the next forward(save = true),
   // `saved_drop` is what that forward used -- backward() regenerates the same masks from it
   DropCfg next_drop = drop_off(), saved_drop = drop_off();

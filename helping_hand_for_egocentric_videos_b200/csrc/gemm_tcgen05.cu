@@ -33,18 +33,29 @@ constexpr int STAGE_LD = 33;  // per-warp transpose buffer: 32 rows x 33 words
 // DEEP_EPI (the QuickGELU epilogue of the 2-SM path): a 4-slot store ring per epilogue warp and one operand stage fewer
 // (same shared-memory total).  A/B on one box: fc1 43.3 -> 41.8 ms per step; the plain-bias GEMMs prefer the sixth
 // operand stage (qkv 61.7 -> 62.6 ms with the deep ring), so they keep 2 slots.
-template <int BLOCK_N, bool TWOSM = false, bool DEEP_EPI = false>
+// RES (the residual + LayerNorm-statistics epilogue): a per-warp ring of RES_SLOTS fp32 boxes (32 rows x 32 columns, 4 KB)
+// that the residual tile streams through (TMA load -> add in place -> TMA store), paid for with two operand stages.
+template <int BLOCK_N, bool TWOSM = false, bool DEEP_EPI = false, bool RES = false, bool LNF = false>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;  // per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256 && !TWOSM) ? 4 : ((TWOSM && DEEP_EPI) ? 5 : 6);
+  static constexpr int RES_SLOTS = 4;
+  static constexpr int RES_BYTES = RES ? 4 * RES_SLOTS * 4096 : 0;
+  static constexpr int STAGES = RES ? ((BLOCK_N == 256 && !TWOSM) ? 2 : 4)
+                                    : ((BLOCK_N == 256 && !TWOSM) ? 4 : ((TWOSM && DEEP_EPI) ? 5 : 6));
   static constexpr int EPI_SLOTS = (TWOSM && DEEP_EPI) ? 4 : 2;      // per-warp ring of 32-row x 128-byte store slots
   static constexpr int EPI_BYTES = 4 * EPI_SLOTS * 4096;            // (>= the 4 x 32 x 33 words of the direct path)
-  static constexpr int BIAS_BYTES = BLOCK_N * 4;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int BIAS_BYTES = (LNF ? 2 : 1) * BLOCK_N * 4;    // bias tile (+ column-sum tile: LayerNorm-folded GEMMs)
+  static constexpr int BAR_BYTES = RES ? 384 : 256;
+  // The dynamic shared-memory window is declared __align__(1024) and there is no static shared memory in this kernel,
+  // so the round-up below is normally a no-op; the slack is kept wherever the budget allows, and the one plan that
+  // cannot afford it (folded LayerNorm on 256-wide tiles) is guarded by a device-side bounds check (traps).
+  static constexpr int ALIGN_SLACK = (LNF && BLOCK_N == 256) ? 0 : 1024;
+  static constexpr int SMEM_BYTES = ALIGN_SLACK + STAGES * STAGE_BYTES + EPI_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: power of two
+  static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
+  static_assert((2 * STAGES + 4 + (RES ? 4 * RES_SLOTS : 0)) * 8 + 4 <= BAR_BYTES, "barrier region too small");
 };
 
 struct GemmArgs {
@@ -54,6 +65,15 @@ struct GemmArgs {
   int M, N, K;
   int ldc, ldr;
   int tiles_m, tiles_n;
+  // LayerNorm folded into the contraction (EPI_LN_*): per-row (sum, sum of squares) partials of the un-normalised A
+  // rows [stats_parts][M][2], the column sums of the gamma-scaled weight, 1 / normalised width, eps
+  const float* colsum;
+  const float* stats_in;
+  int stats_parts;
+  float inv_d, eps;
+  // EPI_RES_STATS_BF16: per-row partials of the rows this GEMM writes, [tiles_n][M][2]; write the fp32 sum back in place
+  float* stats_out;
+  int writeback;
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
@@ -95,21 +115,31 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER, bool TWOSM = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_c, const GemmArgs p) {
+            const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, const GemmArgs p) {
   static_assert(!TWOSM || (CLUSTER && TMA_STORE), "the 2-SM MMA path runs as a CTA pair");
-  using C = Cfg<BLOCK_N, TWOSM, EPI == EPI_BIAS_QGELU_BF16>;
-  extern __shared__ uint8_t smem_raw[];
+  constexpr bool QGELU = (EPI == EPI_BIAS_QGELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16);
+  constexpr bool LNF = (EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16);   // LayerNorm folded (consumer side)
+  constexpr bool RES = (EPI == EPI_RES_STATS_BF16);                                  // residual + statistics (producer)
+  static_assert(!(LNF || RES) || TMA_STORE, "the fused-LayerNorm epilogues use bulk-tensor stores");
+  using C = Cfg<BLOCK_N, TWOSM, QGELU, RES, LNF>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if constexpr (C::ALIGN_SLACK == 0) {
+    if (smem != smem_raw) __trap();  // the window was not 1024-byte aligned: this plan has no room for the round-up
+  }
 
   uint8_t* stage_base = smem;
   float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + C::BIAS_BYTES);
+  uint8_t* res_stage = smem + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES;
+  float* bias_s = reinterpret_cast<float*>(res_stage + C::RES_BYTES);
+  float* cs_s = bias_s + BLOCK_N;              // column sums (LNF only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + C::RES_BYTES + C::BIAS_BYTES);
   uint64_t* full_bar = bars;                   // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;      // [STAGES]
   uint64_t* tfull_bar = bars + 2 * C::STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_full = tempty_bar + 2;         // [4 warps][RES_SLOTS] (RES only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + (RES ? 4 * C::RES_SLOTS : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,11 +154,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if constexpr (TMA_STORE) tma_prefetch_desc(&tma_c);
+    if constexpr (RES) tma_prefetch_desc(&tma_r);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], (CLUSTER && !TWOSM) ? 2 : 1);
+    }
+    if constexpr (RES) {
+      for (int s = 0; s < 4 * C::RES_SLOTS; ++s) mbar_init(&res_full[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -243,6 +277,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     int epi_slot = 0;
+    // ---- RES: the fp32 residual tile streams through this warp's ring of 32 x 32 boxes.  Units (32 output columns of
+    // this warp's 32 rows) are numbered g = 0, 1, ... over all tiles of this CTA; unit g lives in slot g % RES_SLOTS and
+    // is fetched RES_SLOTS - 1 units ahead by lane 0.  One bulk group is committed per unit, so "every group but the
+    // newest has finished reading shared memory" frees exactly the slot the next fetch lands in.
+    constexpr int UNITS = BLOCK_N / 32;
+    const uint32_t res_ring = smem_u32(res_stage) + static_cast<uint32_t>(q * C::RES_SLOTS * 4096);
+    uint64_t* const my_res_full = res_full + q * C::RES_SLOTS;
+    uint32_t g_unit = 0;                        // units consumed so far
+    uint32_t pf_seq = 0;                        // units fetched so far (lane 0)
+    int pf_tile = tile_first, pf_unit = 0;      // coordinates of the next unit to fetch
+    auto res_fetch_next = [&]() {               // lane 0: fetch unit pf_seq into its slot
+      if (pf_tile >= total_tiles) return;
+      const int mp = pf_tile / p.tiles_n;
+      const int n_blk = pf_tile - mp * p.tiles_n;
+      const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
+      const uint32_t slot = pf_seq % C::RES_SLOTS;
+      mbar_arrive_expect_tx(&my_res_full[slot], 4096);
+      tma_load_2d(&tma_r, &my_res_full[slot], res_stage + (q * C::RES_SLOTS + slot) * 4096, n_blk * BLOCK_N + pf_unit * 32,
+                  m_blk * BLOCK_M + q * 32);
+      ++pf_seq;
+      if (++pf_unit == UNITS) {
+        pf_unit = 0;
+        pf_tile += tile_step;
+      }
+    };
+    if constexpr (RES) {
+      if (lane == 0) {
+#pragma unroll 1
+        for (int i = 0; i < C::RES_SLOTS - 1; ++i) res_fetch_next();
+      }
+    }
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int mp = tile / p.tiles_n;
       const int n_blk = tile - mp * p.tiles_n;
@@ -254,6 +319,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int c = et; c < BLOCK_N; c += 128) {
         const int col = col0 + c;
         bias_s[c] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        if constexpr (LNF) cs_s[c] = (col < p.N) ? __ldg(p.colsum + col) : 0.0f;
+      }
+      // folded LayerNorm: this thread's row statistics, from the producer's per-column-tile partials
+      float2 ln_rs = make_float2(1.f, 1.f), ln_nm = make_float2(0.f, 0.f);
+      if constexpr (LNF) {
+        const int row = row0 + lane;
+        float s1 = 0.f, s2 = 0.f;
+        if (row < p.M) {
+          for (int i = 0; i < p.stats_parts; ++i) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(i) * p.M + row);
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        const float mu = s1 * p.inv_d;
+        const float rs = rsqrtf(fmaxf(fmaf(s2, p.inv_d, -mu * mu), 0.f) + p.eps);
+        ln_rs = make_float2(rs, rs);
+        ln_nm = make_float2(-mu * rs, -mu * rs);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
 
@@ -261,8 +344,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
+      if constexpr (RES) {
+        // z = acc + bias + residual: bf16 copy (next GEMM's A operand), per-row sums for the folded LayerNorm, and
+        // optionally the fp32 sum written back over the residual (the stream x itself)
+        const uint32_t zring = smem_u32(epi_stage) + static_cast<uint32_t>(q * C::EPI_SLOTS * 4096);
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int u = 0; u < UNITS; ++u) {
+          const uint32_t slot = g_unit % C::RES_SLOTS;
+          mbar_wait(&my_res_full[slot], (g_unit / C::RES_SLOTS) & 1u);
+          const uint32_t rrow = res_ring + slot * 4096u + static_cast<uint32_t>(lane * 128);
+          const uint32_t zrow = zring + static_cast<uint32_t>(epi_slot * 4096 + lane * 128);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(u * 32), r);
+          tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 x4;
+            const uint32_t ra = rrow + ((static_cast<uint32_t>(k) ^ sw) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x4.x), "=f"(x4.y), "=f"(x4.z), "=f"(x4.w) : "r"(ra) : "memory");
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[u * 32 + 4 * k]);
+            float4 v;
+            v.x = (__uint_as_float(r[4 * k + 0]) + b4.x) + x4.x;
+            v.y = (__uint_as_float(r[4 * k + 1]) + b4.y) + x4.y;
+            v.z = (__uint_as_float(r[4 * k + 2]) + b4.z) + x4.z;
+            v.w = (__uint_as_float(r[4 * k + 3]) + b4.w) + x4.w;
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+            if (p.writeback)
+              st_shared_v4(ra, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+            w[2 * k] = pack_bf16x2(v.x, v.y);
+            w[2 * k + 1] = pack_bf16x2(v.z, v.w);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16-byte chunk ((u & 1) * 4 + k) of the 64-column bf16 row, 128B-swizzled
+            st_shared_v4(zrow + ((static_cast<uint32_t>((u & 1) * 4 + k) ^ sw) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2],
+                         w[4 * k + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.writeback) tma_store_2d(&tma_r, res_ring + slot * 4096u, col0 + u * 32, row0);
+            if (u & 1) tma_store_2d(&tma_c, zring + static_cast<uint32_t>(epi_slot * 4096), col0 + (u >> 1) * 64, row0);
+            tma_store_commit();
+            // the slot of unit g - 1 is free once every group but the newest has been read out of shared memory
+            tma_store_wait_read<1>();
+            res_fetch_next();
+          }
+          if (u & 1) epi_slot = (epi_slot + 1 == C::EPI_SLOTS) ? 0 : epi_slot + 1;
+          ++g_unit;
+        }
+        const int row = row0 + lane;
+        if (row < p.M)
+          *reinterpret_cast<float2*>(p.stats_out + (static_cast<size_t>(n_blk) * p.M + row) * 2) = make_float2(s1, s2);
+      } else
       if constexpr (TMA_STORE) {
-        constexpr bool OUT16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16);
+        constexpr bool OUT16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_QGELU_BF16 || LNF);
         constexpr int CH_COLS = OUT16 ? 64 : 32;  // one chunk = 128 bytes per row
         const uint32_t ring = smem_u32(epi_stage) + static_cast<uint32_t>(q * C::EPI_SLOTS * 4096);
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -287,9 +426,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                        __uint_as_float(r[j + 1]) + bias_s[c * 64 + h * 32 + j + 1]);
                 if constexpr (EPI == EPI_BIAS_QGELU_BF16) v = make_float2(quick_gelu(v.x), quick_gelu(v.y));
 #else
-                float2 v = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
-                                      *reinterpret_cast<const float2*>(&bias_s[c * 64 + h * 32 + j]));
-                if constexpr (EPI == EPI_BIAS_QGELU_BF16) v = quick_gelu2(v);
+                float2 v;
+                if constexpr (LNF) {  // rstd * acc + (bias' - rstd * mean * colsum)
+                  const float2 t = __ffma2_rn(*reinterpret_cast<const float2*>(&cs_s[c * 64 + h * 32 + j]), ln_nm,
+                                              *reinterpret_cast<const float2*>(&bias_s[c * 64 + h * 32 + j]));
+                  v = __ffma2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), ln_rs, t);
+                } else {
+                  v = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                 *reinterpret_cast<const float2*>(&bias_s[c * 64 + h * 32 + j]));
+                }
+                if constexpr (QGELU) v = quick_gelu2(v);
 #endif
                 w[j >> 1] = pack_bf16x2(v.x, v.y);
               }
@@ -443,8 +589,10 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int cols, int ld, in
 }
 
 template <int BLOCK_N, int EPI, bool TMA_STORE, bool CLUSTER, bool TWOSM = false>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& args, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, TWOSM, EPI == EPI_BIAS_QGELU_BF16>;
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, const GemmArgs& args,
+           cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, TWOSM, EPI == EPI_BIAS_QGELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16, EPI == EPI_RES_STATS_BF16,
+                EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16>;
   static bool configured = false;
   auto kern = gemm_kernel<BLOCK_N, EPI, TMA_STORE, CLUSTER, TWOSM>;
   if (!configured) {
@@ -467,92 +615,144 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, args));
+    HH_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tr, args));
     return 0;
   }
   const int total = args.tiles_m * args.tiles_n;
   int grid = num_sms();
   if (grid > total) grid = total;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, args);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, tr, args);
   HH_CHECK_LAUNCH("gemm_kernel");
   return 0;
 }
 
 template <int BLOCK_N>
-int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, bool tma_store, bool cluster,
-                 bool twosm, const GemmArgs& args, int epi, cudaStream_t stream) {
+int dispatch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr, bool tma_store,
+                 bool cluster, bool twosm, const GemmArgs& args, int epi, cudaStream_t stream) {
   if constexpr (BLOCK_N == 256) {
     if (tma_store && cluster && twosm) {
       switch (epi) {
-        case EPI_BIAS_BF16: return launch<256, EPI_BIAS_BF16, true, true, true>(ta, tb, tc, args, stream);
-        case EPI_BIAS_QGELU_BF16: return launch<256, EPI_BIAS_QGELU_BF16, true, true, true>(ta, tb, tc, args, stream);
-        case EPI_BIAS_F32: return launch<256, EPI_BIAS_F32, true, true, true>(ta, tb, tc, args, stream);
+        case EPI_BIAS_BF16: return launch<256, EPI_BIAS_BF16, true, true, true>(ta, tb, tc, tr, args, stream);
+        case EPI_BIAS_QGELU_BF16: return launch<256, EPI_BIAS_QGELU_BF16, true, true, true>(ta, tb, tc, tr, args, stream);
+        case EPI_BIAS_F32: return launch<256, EPI_BIAS_F32, true, true, true>(ta, tb, tc, tr, args, stream);
+        case EPI_LN_BIAS_BF16: return launch<256, EPI_LN_BIAS_BF16, true, true, true>(ta, tb, tc, tr, args, stream);
+        case EPI_LN_BIAS_QGELU_BF16:
+          return launch<256, EPI_LN_BIAS_QGELU_BF16, true, true, true>(ta, tb, tc, tr, args, stream);
+        case EPI_RES_STATS_BF16: return launch<256, EPI_RES_STATS_BF16, true, true, true>(ta, tb, tc, tr, args, stream);
       }
     }
   }
+  if (epi == EPI_RES_STATS_BF16) {  // outside the 2-SM path the residual epilogue runs unclustered on 128-wide tiles
+    if constexpr (BLOCK_N == 128) {
+      if (tma_store && !cluster) return launch<128, EPI_RES_STATS_BF16, true, false>(ta, tb, tc, tr, args, stream);
+    }
+    return fail(-2, "gemm_bf16: residual-statistics epilogue: unsupported tile configuration");
+  }
   if (tma_store && cluster) {
     switch (epi) {
-      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, true>(ta, tb, tc, args, stream);
-      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, true>(ta, tb, tc, args, stream);
-      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, true>(ta, tb, tc, args, stream);
+      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, true>(ta, tb, tc, tr, args, stream);
+      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, true>(ta, tb, tc, tr, args, stream);
+      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, true>(ta, tb, tc, tr, args, stream);
+      case EPI_LN_BIAS_BF16: return launch<BLOCK_N, EPI_LN_BIAS_BF16, true, true>(ta, tb, tc, tr, args, stream);
+      case EPI_LN_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_LN_BIAS_QGELU_BF16, true, true>(ta, tb, tc, tr, args, stream);
     }
   }
   if (tma_store) {
     switch (epi) {
-      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, false>(ta, tb, tc, args, stream);
-      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, false>(ta, tb, tc, args, stream);
-      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, false>(ta, tb, tc, args, stream);
+      case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, true, false>(ta, tb, tc, tr, args, stream);
+      case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, true, false>(ta, tb, tc, tr, args, stream);
+      case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, true, false>(ta, tb, tc, tr, args, stream);
+      case EPI_LN_BIAS_BF16: return launch<BLOCK_N, EPI_LN_BIAS_BF16, true, false>(ta, tb, tc, tr, args, stream);
+      case EPI_LN_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_LN_BIAS_QGELU_BF16, true, false>(ta, tb, tc, tr, args, stream);
     }
   }
   switch (epi) {
-    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, false, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, false, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32, false, false>(ta, tb, tc, args, stream);
-    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, false, false>(ta, tb, tc, args, stream);
+    case EPI_BIAS_BF16: return launch<BLOCK_N, EPI_BIAS_BF16, false, false>(ta, tb, tc, tr, args, stream);
+    case EPI_BIAS_QGELU_BF16: return launch<BLOCK_N, EPI_BIAS_QGELU_BF16, false, false>(ta, tb, tc, tr, args, stream);
+    case EPI_BIAS_RES_F32: return launch<BLOCK_N, EPI_BIAS_RES_F32, false, false>(ta, tb, tc, tr, args, stream);
+    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, false, false>(ta, tb, tc, tr, args, stream);
   }
-  return fail(-2, "gemm_bf16: unknown epilogue");
+  return fail(-2, "gemm_bf16: unknown epilogue or unsupported output alignment for a fused-LayerNorm epilogue");
+}
+
+// Tile plan shared by the launcher and by callers that size the statistics buffer.
+struct TilePlan {
+  int bn, tiles_m, tiles_n;
+  bool cluster, twosm;
+};
+TilePlan plan_tiles(int M, int N, int epilogue, bool tma_store) {
+  TilePlan t;
+  // Tile width: 256 for the wide encoder GEMMs; 128 when N is small or the 256-wide grid would leave SMs idle.
+  t.tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  t.bn = 256;
+  if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || t.tiles_m * ((N + 255) / 256) < num_sms()) t.bn = 128;
+  // CTA pairs sharing the W tile (multicast) once there are enough row tiles to pair up
+  static const bool cluster_ok = std::getenv("HH_GEMM_NO_CLUSTER") == nullptr;
+  t.cluster = cluster_ok && tma_store && t.tiles_m >= num_sms() / 2 && (num_sms() % 2 == 0);
+  // CTA pairs on one 256-row MMA (cta_group::2) for the wide tiles; HH_GEMM_1SM=1 keeps the multicast 1-SM pairs
+  static const bool twosm_ok = std::getenv("HH_GEMM_1SM") == nullptr;
+  t.twosm = t.cluster && twosm_ok && t.bn == 256;
+  if (epilogue == EPI_RES_STATS_BF16 && !t.twosm) {  // its shared-memory plan exists for 2-SM 256-wide and plain 128-wide tiles
+    t.bn = 128;
+    t.cluster = false;
+  }
+  t.tiles_n = (N + t.bn - 1) / t.bn;
+  return t;
 }
 
 }  // namespace
 
-int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
-              const float* residual, int ldr, int M, int N, int K, int epilogue, cudaStream_t stream) {
+int gemm_stats_parts(int M, int N) { return plan_tiles(M, N, EPI_RES_STATS_BF16, true).tiles_n; }
+
+int gemm_bf16_fused(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
+                    float* residual, int ldr, int M, int N, int K, int epilogue, const GemmFuse& fuse,
+                    cudaStream_t stream) {
   HH_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem");
   HH_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: lda/ldw must be multiples of 8 elements (16-byte TMA strides)");
   HH_REQUIRE(K % 8 == 0, "gemm_bf16: K must be a multiple of 8");
   HH_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
              "gemm_bf16: A and W must be 16-byte aligned");
-  const bool out_bf16 = (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_QGELU_BF16);
+  const bool lnf = (epilogue == EPI_LN_BIAS_BF16 || epilogue == EPI_LN_BIAS_QGELU_BF16);
+  const bool res = (epilogue == EPI_RES_STATS_BF16);
+  const bool out_bf16 = (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_QGELU_BF16 || lnf || res);
   if (out_bf16) {
     HH_REQUIRE(ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "gemm_bf16: bf16 output needs even ldc");
   }
   if (epilogue == EPI_BIAS_RES_F32) HH_REQUIRE(residual != nullptr, "gemm_bf16: residual epilogue without residual");
 
-  // Tile width: 256 for the wide encoder GEMMs; 128 when N is small or the 256-wide grid would leave SMs idle.
-  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
-  int bn = 256;
-  if (N <= 128 || (N % 256 != 0 && N % 128 == 0) || tiles_m * ((N + 255) / 256) < num_sms()) bn = 128;
-
   // bulk-tensor stores need a 16-byte aligned base and row pitch; the residual epilogue reads while it writes
   const int esz = out_bf16 ? 2 : 4;
   const bool tma_store = epilogue != EPI_BIAS_RES_F32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                          (static_cast<size_t>(ldc) * esz) % 16 == 0;
-  // CTA pairs sharing the W tile (multicast) once there are enough row tiles to pair up
-  static const bool cluster_ok = std::getenv("HH_GEMM_NO_CLUSTER") == nullptr;
-  const bool cluster = cluster_ok && tma_store && tiles_m >= num_sms() / 2 && (num_sms() % 2 == 0);
-  // CTA pairs on one 256-row MMA (cta_group::2) for the wide tiles; HH_GEMM_1SM=1 keeps the multicast 1-SM pairs
-  static const bool twosm_ok = std::getenv("HH_GEMM_1SM") == nullptr;
-  const bool twosm = cluster && twosm_ok && bn == 256;
-  CUtensorMap ta, tb, tc;
+  if (lnf) {
+    HH_REQUIRE(tma_store, "gemm_bf16: folded-LayerNorm epilogue needs a 16-byte aligned output and row pitch");
+    HH_REQUIRE(fuse.colsum && fuse.stats_in && fuse.stats_parts > 0 && fuse.norm_dim > 0,
+               "gemm_bf16: folded-LayerNorm epilogue without colsum / statistics");
+  }
+  if (res) {
+    HH_REQUIRE(tma_store, "gemm_bf16: residual-statistics epilogue needs a 16-byte aligned output and row pitch");
+    HH_REQUIRE(residual && fuse.stats_out, "gemm_bf16: residual-statistics epilogue without residual / statistics buffer");
+    HH_REQUIRE((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % 4 == 0,
+               "gemm_bf16: residual must be 16-byte aligned with a 16-byte multiple row pitch");
+  }
+  const TilePlan t = plan_tiles(M, N, epilogue, tma_store);
+  const int bn = t.bn;
+  CUtensorMap ta, tb, tc, tr;
   int rc = make_tmap(&ta, A, M, K, lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&tb, W, N, K, ldw, cluster ? bn / 2 : bn);
+  rc = make_tmap(&tb, W, N, K, ldw, t.cluster ? bn / 2 : bn);
   if (rc) return rc;
   if (tma_store) {
     rc = make_tmap(&tc, out, M, N, ldc, 32, esz);
     if (rc) return rc;
   } else {
     tc = ta;
+  }
+  if (res) {
+    rc = make_tmap(&tr, residual, M, N, ldr, 32, 4);
+    if (rc) return rc;
+  } else {
+    tr = ta;
   }
 
   GemmArgs args;
@@ -564,10 +764,24 @@ int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc
   args.K = K;
   args.ldc = ldc;
   args.ldr = ldr;
-  args.tiles_m = tiles_m;
-  args.tiles_n = (N + bn - 1) / bn;
-  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tma_store, cluster, twosm, args, epilogue, stream);
-  return dispatch_epi<128>(ta, tb, tc, tma_store, cluster, false, args, epilogue, stream);
+  args.tiles_m = t.tiles_m;
+  args.tiles_n = t.tiles_n;
+  args.colsum = fuse.colsum;
+  args.stats_in = fuse.stats_in;
+  args.stats_parts = fuse.stats_parts;
+  args.inv_d = fuse.norm_dim > 0 ? 1.0f / static_cast<float>(fuse.norm_dim) : 0.f;
+  args.eps = fuse.eps;
+  args.stats_out = fuse.stats_out;
+  args.writeback = fuse.writeback;
+  if (bn == 256) return dispatch_epi<256>(ta, tb, tc, tr, tma_store, t.cluster, t.twosm, args, epilogue, stream);
+  return dispatch_epi<128>(ta, tb, tc, tr, tma_store, t.cluster, false, args, epilogue, stream);
+}
+
+int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
+              const float* residual, int ldr, int M, int N, int K, int epilogue, cudaStream_t stream) {
+  HH_REQUIRE(epilogue >= EPI_BIAS_BF16 && epilogue <= EPI_BIAS_F32, "gemm_bf16: unknown epilogue");
+  return gemm_bf16_fused(A, lda, W, ldw, out, ldc, bias, const_cast<float*>(residual), ldr, M, N, K, epilogue, GemmFuse{},
+                         stream);
 }
 
 }  // namespace hh

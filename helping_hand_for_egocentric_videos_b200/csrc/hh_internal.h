@@ -44,7 +44,29 @@ enum GemmEpilogue {
   EPI_BIAS_QGELU_BF16 = 1,  // out bf16 = quickgelu(acc + bias)
   EPI_BIAS_RES_F32 = 2,     // out f32  = acc + bias + residual (residual may alias out)
   EPI_BIAS_F32 = 3,         // out f32  = acc + bias
+  // LayerNorm folded into the contraction (GemmFuse): A holds the UN-normalised rows z (bf16), W the gamma-scaled
+  // weight; out = act(rstd * (acc - mean * colsum) + bias') with mean / rstd from the producer's row statistics
+  EPI_LN_BIAS_BF16 = 4,
+  EPI_LN_BIAS_QGELU_BF16 = 5,
+  // out bf16 = z = acc + bias + residual (fp32), per-row (sum z, sum z^2) partials per column tile, optionally
+  // residual <- z in place (fp32): the producer side of the folded LayerNorm
+  EPI_RES_STATS_BF16 = 6,
 };
+// Extra operands of the fused-LayerNorm epilogues (model/LaviLa.py:353-388: norm1/2/3 + residual adds).
+struct GemmFuse {
+  const float* colsum = nullptr;    // EPI_LN_*: fp32 [N], sum_k W'[n, k] of the bf16 weight actually multiplied
+  const float* stats_in = nullptr;  // EPI_LN_*: fp32 [parts][M][2]
+  int stats_parts = 0;
+  int norm_dim = 0;                 // width the statistics were taken over (= K)
+  float eps = 0.f;
+  float* stats_out = nullptr;       // EPI_RES_STATS_BF16: fp32 [gemm_stats_parts(M, N)][M][2]
+  int writeback = 0;                // EPI_RES_STATS_BF16: residual <- acc + bias + residual (fp32, in place)
+};
+// Number of column tiles (= statistics partials per row) EPI_RES_STATS_BF16 uses for an [M, N] output.
+int gemm_stats_parts(int M, int N);
+int gemm_bf16_fused(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
+                    float* residual, int ldr, int M, int N, int K, int epilogue, const GemmFuse& fuse,
+                    cudaStream_t stream);
 // C[M,N] = epilogue(A[M,K] * W[N,K]^T); A, W bf16 with K contiguous. bias fp32 [N] or nullptr.
 int gemm_bf16(const bf16* A, int lda, const bf16* W, int ldw, void* out, int ldc, const float* bias,
               const float* residual, int ldr, int M, int N, int K, int epilogue, cudaStream_t stream);
@@ -76,8 +98,11 @@ int im2col_patches(const float* video, bf16* out, int BT, int H, int W, int p, i
 int im2col_patches_u8(const uint8_t* frames, const float* mean, const float* stdv, bf16* out, int BT, int H, int W, int p,
                       int Kp, cudaStream_t stream);
 // x[b, 0] = LN(cls + pos[0]); x[b, 1 + f*n + q] = LN(tok[(b*T+f)*n + q] + pos[1+q] + temporal[f]);  eps 1e-5
+// Optional (both or neither): z16 bf16 [B*N, D] = bf16(x) and stats fp32 [B*N][2] = per-row (sum x, sum x^2) -- the
+// operands of the first folded-LayerNorm GEMM (one statistics partial per row).
 int assemble_tokens_ln(const float* tok, const float* cls, const float* pos, const float* temporal, const float* w,
-                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream);
+                       const float* b, float eps, float* x, int B, int T, int n, int D, cudaStream_t stream,
+                       bf16* z16 = nullptr, float* stats = nullptr);
 
 // ---------------------------------------------------------------- divided space-time attention (attn_*.cu)
 // qkv bf16 [B*N, 3*D] (q pre-scaled), N = 1 + T*n, heads of 64. out bf16 [B*N, D]; patch rows only.
@@ -132,6 +157,10 @@ int f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t stream);
 // weight packing: dst bf16 [rows, cols_out] = src fp32 [rows, cols_in] (zero padded), first `scaled_rows` rows * scale
 int pack_weight_bf16(const float* src, bf16* dst, int rows, int cols_in, int cols_out, int scaled_rows, float scale,
                      cudaStream_t stream);
+// LayerNorm(gamma, beta) folded into the Linear (W fp32 [rows, K], bias may be null) that follows it: Wf bf16 [rows, K],
+// colsum fp32 [rows], bias_f fp32 [rows]; the first `scaled_rows` rows (and their bias) are multiplied by `scale`.
+int fold_ln_weight(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                   float* bias_f, int rows, int K, int scaled_rows, float scale, cudaStream_t stream);
 // dst[i] = src[i] * (i < scaled ? scale : 1)
 int scale_copy_f32(const float* src, float* dst, size_t n, size_t scaled, float scale, cudaStream_t stream);
 // dst[r, :cols] = src[r, col0 : col0+cols]  (src row stride lds)

@@ -146,6 +146,35 @@ pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int ro
   }
 }
 
+// LayerNorm folded into the following nn.Linear (model/LaviLa.py:353,372,388): with z the un-normalised row,
+//   Linear(LN(z)) = rstd * (z W'^T - mean * colsum) + bias',  W'[r,k] = W[r,k] gamma[k],  bias'[r] = bias[r] + sum_k W[r,k] beta[k],
+// colsum[r] = sum_k W'[r,k] taken over the bf16-ROUNDED W' (the values the tensor cores multiply), so that a constant row
+// z = c maps to exactly bias'.  One warp per weight row; rows below `scaled_rows` (the q third) also carry `scale`.
+__global__ void __launch_bounds__(256)
+fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ bias, bf16* __restrict__ Wf, float* __restrict__ colsum,
+                      float* __restrict__ bias_f, int rows, int K, int scaled_rows, float scale) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float sc = r < scaled_rows ? scale : 1.f;
+  const float* wr = W + static_cast<size_t>(r) * K;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = wr[k];
+    const bf16 wf = __float2bfloat16(w * gamma[k] * sc);
+    Wf[static_cast<size_t>(r) * K + k] = wf;
+    cs += __bfloat162float(wf);
+    bb = fmaf(w, beta[k], bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[r] = cs;
+    bias_f[r] = ((bias ? bias[r] : 0.f) + bb) * sc;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n, size_t scaled, float scale) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -204,6 +233,15 @@ int pack_weight_bf16(const float* src, bf16* dst, int rows, int cols_in, int col
   pack_weight_kernel<<<grid_for(static_cast<long long>(rows) * cols_out), 256, 0, stream>>>(src, dst, rows, cols_in,
                                                                                           cols_out, scaled_rows, scale);
   HH_CHECK_LAUNCH("pack_weight_kernel");
+  return 0;
+}
+
+int fold_ln_weight(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* colsum,
+                   float* bias_f, int rows, int K, int scaled_rows, float scale, cudaStream_t stream) {
+  HH_REQUIRE(rows > 0 && K > 0 && W && gamma && beta && Wf && colsum && bias_f, "fold_ln_weight: bad arguments");
+  fold_ln_weight_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(W, gamma, beta, bias, Wf, colsum, bias_f, rows, K, scaled_rows,
+                                                           scale);
+  HH_CHECK_LAUNCH("fold_ln_weight_kernel");
   return 0;
 }
 

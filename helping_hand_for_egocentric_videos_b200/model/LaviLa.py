@@ -15,6 +15,7 @@ section 8f, row 1) is likewise one call (hh_text_forward) over parameter contain
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from functools import partial
 
@@ -86,24 +87,68 @@ class SpaceTimeBlock(nn.Module):
 class _ParamSync:
     """Pushes nn.Parameters into the C engine when (and only when) they changed: a tensor is re-sent if its storage
     pointer or its in-place version counter differs from what was last uploaded (load_state_dict, .to(),
-    inflate_positional_embeds, optimizer steps all trip one of the two)."""
+    inflate_positional_embeds, optimizer steps all trip one of the two).
+
+    Writes through ``param.data`` (``p.data.copy_(...)``, the pattern of reference model/LaviLa.py:164-170, EMA updates,
+    ``clamp_`` via .data) do NOT bump the version counter: call ``module.mark_dirty()`` after them.  load_state_dict and
+    every ``_apply`` (.to / .cuda / .float) mark the module dirty by themselves.  HH_PARAM_CHECKSUM=1 additionally
+    compares a per-tensor checksum on every sync (debug aid: one small reduction per parameter per forward)."""
 
     def __init__(self):
         self.seen = {}
+        self.checks = {}
+        self.debug = bool(int(os.environ.get("HH_PARAM_CHECKSUM", "0") or 0))
+
+    def clear(self):
+        self.seen.clear()
+        self.checks.clear()
 
     def sync(self, named, setter):
         for key, t in named:
             tag = (t.data_ptr(), t._version, t.dtype)
             if self.seen.get(key) == tag:
-                continue
+                if not self.debug:
+                    continue
+                chk = float(t.detach().double().sum().item())
+                if self.checks.get(key) == chk:
+                    continue
             src = t.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
             setter(key, src)
             self.seen[key] = tag
+            if self.debug:
+                self.checks[key] = float(t.detach().double().sum().item())
 
 
-class SpaceTimeTransformer(nn.Module):
+class _DirtyHooks:
+    """Mixin for the engine-backed modules: everything that can rewrite parameters behind the version counters'
+    back marks the uploaded copies stale."""
+
+    def _sync_states(self):
+        return [v for k, v in vars(self).items() if isinstance(v, _ParamSync)]
+
+    def mark_dirty(self):
+        """Force a re-upload of every parameter on the next forward (needed after writes through ``.data``)."""
+        for st in self._sync_states():
+            st.clear()
+        for m in self.children():
+            if isinstance(m, _DirtyHooks):
+                m.mark_dirty()
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.mark_dirty()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.mark_dirty()
+        return out
+
+
+class SpaceTimeTransformer(_DirtyHooks, nn.Module):
     """Divided space-time ViT, reference model/LaviLa.py:393-581 (only the LaViLa configuration is implemented:
     ``ln_pre=True``, QuickGELU MLP, 'frozen-in-time' residual wiring, qkv_bias=True, no dropout / drop-path)."""
 
@@ -295,7 +340,7 @@ class Transformer(nn.Module):
         raise NotImplementedError("the text blocks run inside hh_text_forward; call CLIP.encode_text")
 
 
-class CLIP(nn.Module):
+class CLIP(_DirtyHooks, nn.Module):
     """Reference model/LaviLa.py:586-687 (dual encoder wrapper)."""
 
     def __init__(self, embed_dim: int, vision_width: int, vision_model: nn.Module, context_length: int,
@@ -340,6 +385,10 @@ class CLIP(nn.Module):
         mask.fill_(float("-inf"))
         mask.triu_(1)
         return mask
+
+    def mark_dirty(self):
+        self._proj_t = None
+        return super().mark_dirty()
 
     def _image_projection_t(self):
         p = self.image_projection
@@ -430,6 +479,11 @@ def _timesformer_clip(patch_size, embed_dim, depth, num_heads, text_width, text_
     vision_model.head = nn.Identity()
     vision_model.pre_logits = nn.Identity()
     vision_model.fc = nn.Identity()
+    if kwargs.get("timesformer_freeze_space"):
+        # reference :74-85 / :135-146: everything the OpenAI-CLIP image tower provides is frozen; the temporal parts
+        # (absent from that checkpoint: timeattn.*, norm3.*, temporal_embed) and cls_token stay trainable
+        for n, p in vision_model.named_parameters():
+            p.requires_grad = ('temporal_embed' in n or 'timeattn' in n or 'norm3' in n or n == 'cls_token')
     kwargs = {k: v for k, v in kwargs.items() if k not in ("pretrained", "text_use_cls_token", "timesformer_freeze_space")}
     return CLIP(embed_dim=project_embed_dim, vision_width=embed_dim, vision_model=vision_model, context_length=77,
                 vocab_size=49408, transformer_width=text_width, transformer_heads=text_heads, transformer_layers=12,
@@ -441,6 +495,7 @@ def CLIP_OPENAI_TIMESFORMER_BASE(num_frames=4, timesformer_gated_xattn=False, dr
                                  use_adapter=False, **kwargs):
     """Reference model/LaviLa.py:55-111 without the OpenAI-CLIP download (:69): weights start random and are expected
     to be overwritten by a LaViLa checkpoint, exactly as run/test_EgoMCQ.py:221-227 does."""
+    kwargs["timesformer_freeze_space"] = timesformer_freeze_space
     return _timesformer_clip(16, 768, 12, 12, 512, 8, num_frames, temperature_init, project_embed_dim,
                              timesformer_gated_xattn, drop_path_rate, use_adapter, kwargs)
 
@@ -449,5 +504,6 @@ def CLIP_OPENAI_TIMESFORMER_LARGE(num_frames=4, timesformer_gated_xattn=False, d
                                   timesformer_freeze_space=False, temperature_init=0.07, project_embed_dim=256,
                                   use_adapter=False, **kwargs):
     """Reference model/LaviLa.py:114-172 without the network access (:130)."""
+    kwargs["timesformer_freeze_space"] = timesformer_freeze_space
     return _timesformer_clip(14, 1024, 24, 16, 768, 12, num_frames, temperature_init, project_embed_dim,
                              timesformer_gated_xattn, drop_path_rate, use_adapter, kwargs)

@@ -33,8 +33,8 @@ def sim_matrix(a, b, eps=1e-8, norm=True):
         if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
             return _SimMatrixFn.apply(a.float().contiguous(), b.float().contiguous(), eps)
         return ops.sim_matrix(a, b, eps)
-    if a.dim() == 3:
-        return torch.stack([ops.sim_matrix(x, y, eps) for x, y in zip(a, b)])
+    if a.dim() == 3:       # bmm form: one scoring launch per batch entry, each carrying its own backward
+        return torch.stack([sim_matrix(x, y, eps) for x, y in zip(a, b)])
     raise ValueError("sim_matrix expects 2-D or 3-D inputs")
 
 

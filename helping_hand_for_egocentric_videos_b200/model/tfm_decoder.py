@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from .. import ops
-from .LaviLa import _ParamSync
+from .LaviLa import _DirtyHooks, _ParamSync
 
 
 class _LinearFn(torch.autograd.Function):
@@ -88,6 +88,10 @@ class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, features, *params):
         hs, logits, boxes = module._run_engine(features, train=True)
+        # the engine holds one activation set: stamp this graph with the forward's ordinal so that a backward issued
+        # after ANOTHER forward of the same module (two clips then a summed backward, ...) fails instead of silently
+        # differentiating the wrong activations / dropout masks
+        ctx.generation = L.load().hh_decoder_generation(module._engine())
         ctx.module = module
         ctx.keys = [k for k, _ in module._engine_params()]
         ctx.shapes = [tuple(p.shape) for p in params]
@@ -104,8 +108,8 @@ class _DecoderFn(torch.autograd.Function):
         def prep(g):
             return None if g is None else (g if (g.dtype == torch.float32 and g.is_contiguous()) else g.float().contiguous())
         d_hs, d_boxes = prep(d_hs), prep(d_boxes)
-        L.check(lib.hh_decoder_backward(m._engine(), L.ptr(hs), L.ptr(boxes), L.ptr(d_hs), L.ptr(d_boxes), L.stream_ptr()),
-                "hh_decoder_backward")
+        L.check(lib.hh_decoder_backward_checked(m._engine(), ctx.generation, L.ptr(hs), L.ptr(boxes), L.ptr(d_hs),
+                                                L.ptr(d_boxes), L.stream_ptr()), "hh_decoder_backward")
         grads = []
         for key, shp, need in zip(ctx.keys, ctx.shapes, ctx.needs_input_grad[2:]):
             if not need:
@@ -184,7 +188,7 @@ class Cross_Attention(nn.Module):
         self.dropout_p = dropout
 
 
-class ObjDecoder(nn.Module):
+class ObjDecoder(_DirtyHooks, nn.Module):
     """Reference :111-241."""
 
     def __init__(self, transformer, num_classes, num_queries, feature_dim=768, aux_loss=False, pred_traj=True,
@@ -331,6 +335,13 @@ class ObjDecoder(nn.Module):
         self.sync_weights()
         params = [p for _, p in self._engine_params()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if self.class_embed.weight.requires_grad and not getattr(self, "_warned_logits", False):
+                # the reference criterion has no class loss (run/train.py:471, exclude_class=True): the hand-written
+                # backward leaves class_embed.* at zero and pred_logits is a constant of the graph -- say so once
+                # instead of letting a 'labels' loss train nothing in silence
+                warnings.warn("ObjDecoder (B200): pred_logits carries no gradient (the reference training loop has no "
+                              "class loss); a loss built on pred_logits will not train the decoder", stacklevel=2)
+                self._warned_logits = True
             hs, logits, boxes = _DecoderFn.apply(self, features, *params)
         else:
             with torch.no_grad():  # train() mode drops activations even when no gradient is recorded, as nn.Dropout does

@@ -38,12 +38,62 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None
     return out
 
 
+def fold_layernorm_weight(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: torch.Tensor | None = None,
+                          scaled_rows: int = 0, scale: float = 1.0):
+    """LayerNorm(gamma, beta) folded into the Linear(w, bias) that follows it -> (Wf bf16 [N,K], colsum [N], bias_f [N])."""
+    w32, g32, b32 = _f32(w), _f32(gamma), _f32(beta)
+    bias32 = _f32(bias) if bias is not None else None
+    N, K = w32.shape
+    wf = torch.empty(N, K, dtype=torch.bfloat16, device=w.device)
+    cs = torch.empty(N, dtype=torch.float32, device=w.device)
+    bf = torch.empty(N, dtype=torch.float32, device=w.device)
+    L.check(L.load().hh_fold_layernorm_weight(L.ptr(w32), L.ptr(g32), L.ptr(b32), L.ptr(bias32), N, K, scaled_rows, scale,
+                                              L.ptr(wf), L.ptr(cs), L.ptr(bf), L.stream_ptr()), "hh_fold_layernorm_weight")
+    return wf, cs, bf
+
+
+def gemm_bf16_res_stats(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, residual: torch.Tensor,
+                        writeback: bool = False):
+    """Producer side of the folded LayerNorm: z = a w^T + bias + residual -> (z bf16 [M,N], stats fp32 [parts, M, 2]);
+    `residual` (fp32 [M,N]) receives z in place when `writeback`."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and residual.dtype == torch.float32
+    a, w = _c(a), _c(w)
+    assert residual.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert residual.shape == (M, N)
+    parts = L.load().hh_gemm_stats_parts(M, N)
+    z = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    stats = torch.zeros(parts, M, 2, dtype=torch.float32, device=a.device)
+    bias32 = _f32(bias) if bias is not None else None
+    L.check(L.load().hh_gemm_bf16_res_stats(L.ptr(a), K, L.ptr(w), K, L.ptr(z), N, L.ptr(bias32), L.ptr(residual), N,
+                                            1 if writeback else 0, L.ptr(stats), M, N, K, L.stream_ptr()),
+            "hh_gemm_bf16_res_stats")
+    return z, stats
+
+
+def gemm_bf16_ln(z: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, colsum: torch.Tensor, stats: torch.Tensor,
+                 eps: float, qgelu: bool = False) -> torch.Tensor:
+    """Consumer side: act(Linear(LayerNorm(z))) with the norm folded into (wf, colsum, bias_f); stats [parts, M, 2]."""
+    assert z.dtype == torch.bfloat16 and wf.dtype == torch.bfloat16 and stats.dtype == torch.float32
+    z, wf, stats = _c(z), _c(wf), _c(stats)
+    M, K = z.shape
+    N = wf.shape[0]
+    assert stats.dim() == 3 and stats.shape[1] == M and stats.shape[2] == 2
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=z.device)
+    b32, c32 = _f32(bias_f), _f32(colsum)
+    L.check(L.load().hh_gemm_bf16_ln(L.ptr(z), K, L.ptr(wf), K, L.ptr(out), N, L.ptr(b32), L.ptr(c32), L.ptr(stats),
+                                     stats.shape[0], K, eps, M, N, K, 1 if qgelu else 0, L.stream_ptr()), "hh_gemm_bf16_ln")
+    return out
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, want_f32=True, want_bf16=False):
     x = _f32(x)
     M, D = x.shape
     o32 = torch.empty_like(x) if want_f32 else None
     o16 = torch.empty(M, D, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    L.check(L.load().hh_layernorm(L.ptr(x), D, L.ptr(_f32(w)), L.ptr(_f32(b)), eps, L.ptr(o32), L.ptr(o16), M, D,
+    w32, b32 = _f32(w), _f32(b)     # bound to locals: a converted temporary must outlive the call that reads its pointer
+    L.check(L.load().hh_layernorm(L.ptr(x), D, L.ptr(w32), L.ptr(b32), eps, L.ptr(o32), L.ptr(o16), M, D,
                                   L.stream_ptr()), "hh_layernorm")
     return o32, o16
 
@@ -93,8 +143,10 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None 
     x2 = _f32(x).reshape(-1, shp[-1])
     N, K = weight.shape
     out = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+    w32 = _f32(weight)              # locals keep converted (non-fp32 / non-contiguous) parameters alive across the call
+    b32 = _f32(bias) if bias is not None else None
     if x2.shape[0] > 0:
-        L.check(L.load().hh_linear_f32(L.ptr(x2), K, None, 0, L.ptr(_f32(weight)), L.ptr(_f32(bias)) if bias is not None else None,
+        L.check(L.load().hh_linear_f32(L.ptr(x2), K, None, 0, L.ptr(w32), L.ptr(b32),
                                        None, 0, L.ptr(out), N, x2.shape[0], N, K, act, 1 if in_relu else 0,
                                        L.stream_ptr()), "hh_linear_f32")
     return out.reshape(*shp[:-1], N)

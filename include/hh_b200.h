@@ -111,6 +111,12 @@ int hh_decoder_forward_train(hh_decoder* dec, const float* features, int64_t str
 int hh_decoder_set_dropout(hh_decoder* dec, float p, uint64_t seed, uint32_t offset);
 int hh_decoder_backward(hh_decoder* dec, const float* hs, const float* boxes, const float* d_hs, const float* d_boxes,
                         void* stream);
+/* The engine keeps ONE set of saved activations.  hh_decoder_generation returns the ordinal of the last forward (every
+ * forward, training or not, bumps it); hh_decoder_backward_checked refuses (-2) when `generation` is not that ordinal,
+ * i.e. when another forward ran between the training forward being differentiated and this call. */
+uint64_t hh_decoder_generation(const hh_decoder* dec);
+int hh_decoder_backward_checked(hh_decoder* dec, uint64_t generation, const float* hs, const float* boxes,
+                                const float* d_hs, const float* d_boxes, void* stream);
 int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream);
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
 int hh_decoder_last_launches(const hh_decoder* dec);
@@ -184,6 +190,24 @@ int hh_box_match_cost(const float* pred, const float* tgt, int N, int M, float w
  * 1 bias+QuickGELU->bf16, 2 bias+fp32 residual->fp32, 3 bias->fp32.  (nn.Linear calls of LaviLa.py:249,281,186,189) */
 int hh_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldc, const float* bias,
                  const float* residual, int ldr, int M, int N, int K, int epilogue, void* stream);
+/* LayerNorm folded into the contractions around it (norm1 / norm2 / norm3 + residual adds of SpaceTimeBlock.forward,
+ * model/LaviLa.py:353-388; north_star "fused LayerNorm+bias+GELU epilogues").  With z the UN-normalised row,
+ *   Linear(LayerNorm(z)) = rstd * (z W'^T - mean * colsum) + bias',   W' = W diag(gamma),  bias' = bias + W beta.
+ * hh_fold_layernorm_weight: W fp32 [N,K], gamma / beta fp32 [K], bias fp32 [N] or NULL -> Wf bf16 [N,K], colsum fp32 [N]
+ *   (column sums of the bf16-rounded W'), bias_f fp32 [N]; the first `scaled_rows` rows and their bias also carry `scale`.
+ * hh_gemm_bf16_res_stats (producer): z16 bf16 [M,N] = A W^T + bias + residual (fp32 [M,N], row pitch ldr); per-row
+ *   (sum z, sum z^2) partials, one per column tile: stats fp32 [hh_gemm_stats_parts(M,N)][M][2]; writeback != 0 also stores
+ *   the fp32 sum over `residual` in place (the residual stream itself).
+ * hh_gemm_bf16_ln (consumer): out bf16 [M,N] = act(rstd * (A Wf^T - mean * colsum) + bias_f), mean / rstd per row from
+ *   `parts` statistics partials taken over norm_dim (= K) columns; act = QuickGELU when qgelu != 0. */
+int hh_gemm_stats_parts(int M, int N);
+int hh_fold_layernorm_weight(const float* W, const float* gamma, const float* beta, const float* bias, int N, int K,
+                             int scaled_rows, float scale, void* Wf, float* colsum, float* bias_f, void* stream);
+int hh_gemm_bf16_res_stats(const void* A, int lda, const void* W, int ldw, void* z16, int ldz, const float* bias,
+                           float* residual, int ldr, int writeback, float* stats, int M, int N, int K, void* stream);
+int hh_gemm_bf16_ln(const void* A, int lda, const void* Wf, int ldw, void* out, int ldc, const float* bias_f,
+                    const float* colsum, const float* stats, int parts, int norm_dim, float eps, int M, int N, int K,
+                    int qgelu, void* stream);
 /* LayerNorm rows (fp32 in): optional fp32 and bf16 outputs. */
 int hh_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, float* out_f32, void* out_bf16,
                  int M, int D, void* stream);

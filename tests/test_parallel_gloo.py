@@ -50,6 +50,70 @@ def test_packed_allgather_and_sharded_similarity_world2():
     assert dict(ret) == {0: True, 1: True}
 
 
+class _RefAllGather(torch.autograd.Function):
+    """The reference's AllGather_multi (run/train.py:31-47), restated for the comparison."""
+
+    @staticmethod
+    def forward(ctx, tensor, rank, world):
+        output = [torch.empty_like(tensor) for _ in range(world)]
+        dist.all_gather(output, tensor)
+        ctx.rank, ctx.batch_size = rank, tensor.shape[0]
+        return torch.cat(output, 0)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output[ctx.batch_size * ctx.rank: ctx.batch_size * (ctx.rank + 1)], None, None
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11 + rank)
+        vid = torch.randn(5, 16, generator=g)
+        txt = torch.randn(5, 16, generator=g)
+        tok = torch.randint(0, 99, (5, 7), generator=g)
+        wgt = torch.randn(world * 5, world * 5, generator=torch.Generator().manual_seed(3))   # same on every rank
+
+        def loss_of(gather):
+            v = vid.clone().requires_grad_(True)
+            t = txt.clone().requires_grad_(True)
+            va, ta, ka = gather(v, t, tok)
+            loss = ((ta @ va.t()) * wgt).sum() + (va * va).sum() * (1 + ka.float().mean())
+            loss.backward()
+            return loss.detach(), v.grad, t.grad, ka
+
+        ours = loss_of(lambda v, t, k: parallel.all_gather_packed([v, t, k]))
+        ref = loss_of(lambda v, t, k: (_RefAllGather.apply(v, rank, world), _RefAllGather.apply(t, rank, world),
+                                       _RefAllGather.apply(k, rank, world)))
+        ok = torch.allclose(ours[0], ref[0]) and ours[1] is not None and ours[2] is not None
+        ok = ok and torch.allclose(ours[1], ref[1]) and torch.allclose(ours[2], ref[2]) and torch.equal(ours[3], ref[3])
+        ok = ok and not ours[3].requires_grad
+        # the side-stream form is the same exchange (CPU tensors: executed inline)
+        h = parallel.all_gather_packed_async([vid, tok], slot=1)
+        va, ka = h.wait()
+        ok = ok and torch.equal(va, ours_cat(vid, world)) and torch.equal(ka, ours_cat(tok, world))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def ours_cat(t, world):
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return torch.cat(out, 0)
+
+
+def test_allgather_backward_matches_reference_world2():
+    """the gather must carry gradients exactly like AllGather_multi (local slice of the output gradient)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
 def test_shard_range_covers_everything_once():
     for total in (0, 1, 7, 64, 9668):
         for world in (1, 2, 3, 8):
