@@ -42,12 +42,16 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RES_SLOTS = 4;
   static constexpr int RES_BYTES = RES ? 4 * RES_SLOTS * 4096 : 0;
+#ifdef HH_GEMM_PLAIN_STAGES   // variant builds: sensitivity of the plain epilogues to the operand ring depth
+  static constexpr int STAGES = RES ? ((BLOCK_N == 256 && !TWOSM) ? 2 : 4) : ((BLOCK_N == 256 && !TWOSM) ? 4 : HH_GEMM_PLAIN_STAGES);
+#else
   static constexpr int STAGES = RES ? ((BLOCK_N == 256 && !TWOSM) ? 2 : 4)
                                     : ((BLOCK_N == 256 && !TWOSM) ? 4 : ((TWOSM && DEEP_EPI) ? 5 : 6));
+#endif
   static constexpr int EPI_SLOTS = (TWOSM && DEEP_EPI) ? 4 : 2;      // per-warp ring of 32-row x 128-byte store slots
   static constexpr int EPI_BYTES = 4 * EPI_SLOTS * 4096;            // (>= the 4 x 32 x 33 words of the direct path)
   static constexpr int BIAS_BYTES = (LNF ? 2 : 1) * BLOCK_N * 4;    // bias tile (+ column-sum tile: LayerNorm-folded GEMMs)
-  static constexpr int BAR_BYTES = RES ? 384 : 256;
+  static constexpr int BAR_BYTES = RES ? 512 : 256;
   // The dynamic shared-memory window is declared __align__(1024) and there is no static shared memory in this kernel,
   // so the round-up below is normally a no-op; the slack is kept wherever the budget allows, and the one plan that
   // cannot afford it (folded LayerNorm on 256-wide tiles) is guarded by a device-side bounds check (traps).
@@ -55,7 +59,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = ALIGN_SLACK + STAGES * STAGE_BYTES + EPI_BYTES + RES_BYTES + BIAS_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512: power of two
   static_assert(SMEM_BYTES <= 232448, "shared-memory plan exceeds 227 KB");
-  static_assert((2 * STAGES + 4 + (RES ? 4 * RES_SLOTS : 0)) * 8 + 4 <= BAR_BYTES, "barrier region too small");
+  static_assert((2 * STAGES + 4 + (RES ? 8 * RES_SLOTS : 0)) * 8 + 4 <= BAR_BYTES, "barrier region too small");
 };
 
 struct GemmArgs {
@@ -94,6 +98,20 @@ __device__ __forceinline__ float2 quick_gelu2(float2 x) {
   const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(hx, t, hx);
 }
+
+
+// HH_GEMM_TRACE (variant builds only, tools/build_variant.sh): cycles each role of every CTA spends in its waits, read
+// back with hh_debug_gemm_trace.  Slots per CTA: [0] kernel cycles, producer [1] empty; MMA [2] accumulator-empty [3] full;
+// epilogue warp 0 lane 0 [4] accumulator-full [5] residual-full [6] bulk-store read [7] bias / statistics prologue
+// [8] tiles; epilogue warp 0 lane 1 [9] accumulator-full [10] residual-full.
+#ifdef HH_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[148 * 16];
+#define TR_T0() const long long tr_t0_ = clock64()
+#define TR_ADD(slot) tr_[slot] += static_cast<unsigned long long>(clock64() - tr_t0_)
+#else
+#define TR_T0() do { } while (0)
+#define TR_ADD(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -139,7 +157,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tfull_bar = bars + 2 * C::STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint64_t* res_full = tempty_bar + 2;         // [4 warps][RES_SLOTS] (RES only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + (RES ? 4 * C::RES_SLOTS : 0));
+  uint64_t* res_empty = res_full + (RES ? 4 * C::RES_SLOTS : 0);  // [4 warps][RES_SLOTS] (RES only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + (RES ? 4 * C::RES_SLOTS : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,7 +181,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&empty_bar[s], (CLUSTER && !TWOSM) ? 2 : 1);
     }
     if constexpr (RES) {
-      for (int s = 0; s < 4 * C::RES_SLOTS; ++s) mbar_init(&res_full[s], 1);
+      for (int s = 0; s < 4 * C::RES_SLOTS; ++s) {
+        mbar_init(&res_full[s], 1);
+        mbar_init(&res_empty[s], 1);
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -184,6 +206,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if constexpr (CLUSTER) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef HH_GEMM_TRACE
+  unsigned long long tr_[16] = {};
+  const long long tr_begin_ = clock64();
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -195,7 +221,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int n_blk = tile - mp * p.tiles_n;
         const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          { TR_T0(); mbar_wait(&empty_bar[stage], phase ^ 1u); TR_ADD(1); }
           uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           if constexpr (TWOSM) {  // my A rows + my half of the W tile, into MY smem, signalled on the leader's barrier
@@ -232,11 +258,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        { TR_T0(); mbar_wait(&tempty_bar[acc], acc_phase ^ 1u); TR_ADD(2); }  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          { TR_T0(); mbar_wait(&full_bar[stage], phase); TR_ADD(3); }
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
@@ -269,6 +295,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ residual producer (RES only): lane q feeds epilogue
+    // warp q's ring of fp32 boxes (32 rows x 32 columns), one box per unit, in the order the epilogue consumes them
+    if constexpr (RES) {
+      if (lane < 4) {
+        const int q = lane;
+        uint64_t* const my_full = res_full + q * C::RES_SLOTS;
+        uint64_t* const my_empty = res_empty + q * C::RES_SLOTS;
+        uint8_t* const my_ring = res_stage + q * C::RES_SLOTS * 4096;
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+          const int mp = tile / p.tiles_n;
+          const int n_blk = tile - mp * p.tiles_n;
+          const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
+#pragma unroll 1
+          for (int u = 0; u < BLOCK_N / 32; ++u) {
+            mbar_wait(&my_empty[slot], phase ^ 1u);
+            mbar_arrive_expect_tx(&my_full[slot], 4096);
+            tma_load_2d(&tma_r, &my_full[slot], my_ring + slot * 4096, n_blk * BLOCK_N + u * 32, m_blk * BLOCK_M + q * 32);
+            if (++slot == C::RES_SLOTS) {
+              slot = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
@@ -277,70 +331,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     int epi_slot = 0;
-    // ---- RES: the fp32 residual tile streams through this warp's ring of 32 x 32 boxes.  Units (32 output columns of
-    // this warp's 32 rows) are numbered g = 0, 1, ... over all tiles of this CTA; unit g lives in slot g % RES_SLOTS and
-    // is fetched RES_SLOTS - 1 units ahead by lane 0.  One bulk group is committed per unit, so "every group but the
-    // newest has finished reading shared memory" frees exactly the slot the next fetch lands in.
+    // ---- RES: the fp32 residual tile streams through this warp's ring of 32 x 32 boxes, filled by warp 3.  Units (32
+    // output columns of this warp's 32 rows) are consumed in tile / column order; one bulk group is committed per unit,
+    // so "every group but the newest has finished reading shared memory" frees the slot of the previous unit.
     constexpr int UNITS = BLOCK_N / 32;
     const uint32_t res_ring = smem_u32(res_stage) + static_cast<uint32_t>(q * C::RES_SLOTS * 4096);
     uint64_t* const my_res_full = res_full + q * C::RES_SLOTS;
-    uint32_t g_unit = 0;                        // units consumed so far
-    uint32_t pf_seq = 0;                        // units fetched so far (lane 0)
-    int pf_tile = tile_first, pf_unit = 0;      // coordinates of the next unit to fetch
-    auto res_fetch_next = [&]() {               // lane 0: fetch unit pf_seq into its slot
-      if (pf_tile >= total_tiles) return;
-      const int mp = pf_tile / p.tiles_n;
-      const int n_blk = pf_tile - mp * p.tiles_n;
+    uint64_t* const my_res_empty = res_empty + q * C::RES_SLOTS;
+    int res_slot = 0;
+    uint32_t res_phase = 0;
+    int res_prev = -1;                          // slot whose write-back store is still reading shared memory
+    // ---- per-tile constants are fetched one tile ahead (registers), so their global-load latency hides behind the
+    // previous tile's work: bias / column sums for columns et, et + 128, and this thread's row statistics
+    constexpr int BPT = BLOCK_N / 128;
+    float nb_bias[BPT], nb_cs[BPT];
+    float n_s1 = 0.f, n_s2 = 0.f;
+    auto prefetch_tile_consts = [&](int tile) {
+      if (tile >= total_tiles) return;
+      const int mp = tile / p.tiles_n;
+      const int n_blk = tile - mp * p.tiles_n;
       const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
-      const uint32_t slot = pf_seq % C::RES_SLOTS;
-      mbar_arrive_expect_tx(&my_res_full[slot], 4096);
-      tma_load_2d(&tma_r, &my_res_full[slot], res_stage + (q * C::RES_SLOTS + slot) * 4096, n_blk * BLOCK_N + pf_unit * 32,
-                  m_blk * BLOCK_M + q * 32);
-      ++pf_seq;
-      if (++pf_unit == UNITS) {
-        pf_unit = 0;
-        pf_tile += tile_step;
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) {
+        const int col = n_blk * BLOCK_N + et + i * 128;
+        nb_bias[i] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        if constexpr (LNF) nb_cs[i] = (col < p.N) ? __ldg(p.colsum + col) : 0.0f;
+      }
+      if constexpr (LNF) {
+        const int row = m_blk * BLOCK_M + q * 32 + lane;
+        n_s1 = 0.f;
+        n_s2 = 0.f;
+        if (row < p.M) {
+          float2 t[4] = {};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < p.stats_parts) t[i] = __ldg(reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(i) * p.M + row);
+          for (int i = 4; i < p.stats_parts; ++i) {
+            const float2 e = __ldg(reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(i) * p.M + row);
+            t[0].x += e.x;
+            t[0].y += e.y;
+          }
+          n_s1 = (t[0].x + t[1].x) + (t[2].x + t[3].x);
+          n_s2 = (t[0].y + t[1].y) + (t[2].y + t[3].y);
+        }
       }
     };
-    if constexpr (RES) {
-      if (lane == 0) {
-#pragma unroll 1
-        for (int i = 0; i < C::RES_SLOTS - 1; ++i) res_fetch_next();
-      }
-    }
+    prefetch_tile_consts(tile_first);
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int mp = tile / p.tiles_n;
       const int n_blk = tile - mp * p.tiles_n;
       const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
       const int row0 = m_blk * BLOCK_M + q * 32;
       const int col0 = n_blk * BLOCK_N;
+#ifdef HH_GEMM_TRACE
+      const long long tr_tile0_ = clock64();
+#endif
 
-      // bias tile -> smem (previous tile's readers are done: they passed the trailing named barrier)
-      for (int c = et; c < BLOCK_N; c += 128) {
-        const int col = col0 + c;
-        bias_s[c] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-        if constexpr (LNF) cs_s[c] = (col < p.N) ? __ldg(p.colsum + col) : 0.0f;
+      // bias tile -> smem from the registers fetched one tile ago (the previous tile's readers are done: they passed
+      // the trailing named barrier)
+#pragma unroll
+      for (int i = 0; i < BPT; ++i) {
+        bias_s[et + i * 128] = nb_bias[i];
+        if constexpr (LNF) cs_s[et + i * 128] = nb_cs[i];
       }
       // folded LayerNorm: this thread's row statistics, from the producer's per-column-tile partials
       float2 ln_rs = make_float2(1.f, 1.f), ln_nm = make_float2(0.f, 0.f);
       if constexpr (LNF) {
-        const int row = row0 + lane;
-        float s1 = 0.f, s2 = 0.f;
-        if (row < p.M) {
-          for (int i = 0; i < p.stats_parts; ++i) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(i) * p.M + row);
-            s1 += t.x;
-            s2 += t.y;
-          }
-        }
-        const float mu = s1 * p.inv_d;
-        const float rs = rsqrtf(fmaxf(fmaf(s2, p.inv_d, -mu * mu), 0.f) + p.eps);
+        const float mu = n_s1 * p.inv_d;
+        const float rs = rsqrtf(fmaxf(fmaf(n_s2, p.inv_d, -mu * mu), 0.f) + p.eps);
         ln_rs = make_float2(rs, rs);
         ln_nm = make_float2(-mu * rs, -mu * rs);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      prefetch_tile_consts(tile + tile_step);   // in flight while this tile is processed
+#ifdef HH_GEMM_TRACE
+      tr_[7] += static_cast<unsigned long long>(clock64() - tr_tile0_);
+      tr_[8] += 1;
+#endif
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      { TR_T0(); mbar_wait(&tfull_bar[acc], acc_phase); TR_ADD(4); }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 
@@ -352,12 +421,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int u = 0; u < UNITS; ++u) {
-          const uint32_t slot = g_unit % C::RES_SLOTS;
-          mbar_wait(&my_res_full[slot], (g_unit / C::RES_SLOTS) & 1u);
+          const uint32_t slot = static_cast<uint32_t>(res_slot);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(u * 32), r);   // in flight while the residual box is awaited
+          { TR_T0(); mbar_wait(&my_res_full[slot], res_phase); TR_ADD(5); }
           const uint32_t rrow = res_ring + slot * 4096u + static_cast<uint32_t>(lane * 128);
           const uint32_t zrow = zring + static_cast<uint32_t>(epi_slot * 4096 + lane * 128);
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(u * 32), r);
           tmem_ld_wait();
           uint32_t w[16];
 #pragma unroll
@@ -389,12 +458,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (p.writeback) tma_store_2d(&tma_r, res_ring + slot * 4096u, col0 + u * 32, row0);
             if (u & 1) tma_store_2d(&tma_c, zring + static_cast<uint32_t>(epi_slot * 4096), col0 + (u >> 1) * 64, row0);
             tma_store_commit();
-            // the slot of unit g - 1 is free once every group but the newest has been read out of shared memory
-            tma_store_wait_read<1>();
-            res_fetch_next();
+            // every group but the newest has been read out of shared memory: with write-back that frees the previous
+            // unit's box (and bounds the z ring); without it this unit's box is free as soon as the warp has read it
+            { TR_T0(); tma_store_wait_read<1>(); TR_ADD(6); }
+            if (p.writeback) {
+              if (res_prev >= 0) mbar_arrive(&my_res_empty[res_prev]);
+            } else {
+              mbar_arrive(&my_res_empty[slot]);
+            }
           }
+          res_prev = res_slot;
           if (u & 1) epi_slot = (epi_slot + 1 == C::EPI_SLOTS) ? 0 : epi_slot + 1;
-          ++g_unit;
+          if (++res_slot == C::RES_SLOTS) {
+            res_slot = 0;
+            res_phase ^= 1u;
+          }
         }
         const int row = row0 + lane;
         if (row < p.M)
@@ -408,15 +486,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / CH_COLS; ++c) {
           // the bulk store that last used this slot must have finished reading it
-          if (lane == 0) tma_store_wait_read<C::EPI_SLOTS - 1>();
+          if (lane == 0) { TR_T0(); tma_store_wait_read<C::EPI_SLOTS - 1>(); TR_ADD(6); }
           __syncwarp();
           const uint32_t row_addr = ring + static_cast<uint32_t>(epi_slot * 4096 + lane * 128);
           if constexpr (OUT16) {
+            // both 32-column halves of the chunk are requested before the single wait: two TMEM loads in flight
+            uint32_t rr[2][32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 64), rr[0]);
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 64 + 32), rr[1]);
+            tmem_ld_wait();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              uint32_t r[32];
-              tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 64 + h * 32), r);
-              tmem_ld_wait();
+              const uint32_t(&r)[32] = rr[h];
               uint32_t w[16];
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
@@ -545,6 +626,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     (void)epi_slot;
   }
 
+#ifdef HH_GEMM_TRACE
+  if (blockIdx.x < 148) {
+    unsigned long long* g = g_gemm_trace + blockIdx.x * 16;
+    if (warp == 0 && lane == 0) { g[0] = static_cast<unsigned long long>(clock64() - tr_begin_); g[1] = tr_[1]; }
+    if (warp == 1 && lane == 0) { g[2] = tr_[2]; g[3] = tr_[3]; }
+    if (warp == EPI_WARP0 && lane == 0) { g[4] = tr_[4]; g[5] = tr_[5]; g[6] = tr_[6]; g[7] = tr_[7]; g[8] = tr_[8]; }
+    if (warp == EPI_WARP0 && lane == 1) { g[9] = tr_[4]; g[10] = tr_[5]; }
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if constexpr (CLUSTER) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
@@ -701,6 +791,13 @@ TilePlan plan_tiles(int M, int N, int epilogue, bool tma_store) {
 }
 
 }  // namespace
+
+#ifdef HH_GEMM_TRACE
+extern "C" int hh_debug_gemm_trace(unsigned long long* out, int n) {
+  if (n > 148 * 16) n = 148 * 16;
+  return static_cast<int>(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * n));
+}
+#endif
 
 int gemm_stats_parts(int M, int N) { return plan_tiles(M, N, EPI_RES_STATS_BF16, true).tiles_n; }
 

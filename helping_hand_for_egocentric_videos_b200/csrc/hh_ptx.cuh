@@ -202,13 +202,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* 
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(crd0), "r"(crd1)
       : "memory");
 }
-// mbarrier arrive on the barrier at this offset in CTA `rank` of the cluster.
+// mbarrier arrive on the barrier at this offset in CTA `rank` of the cluster.  Default (CTA-scope release) semantics:
+// what the arrive hands over here is TMEM that the arriving warp has finished reading (tcgen05.wait::ld + tcgen05.fence),
+// no generic-proxy memory; the cluster-scope release form costs a MEMBAR + ERRBAR per call (35 % of the epilogue warps'
+// samples in the round-2 ncu capture of the 2-SM GEMM).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }

@@ -26,6 +26,9 @@ CASES = {
     # BASELINE c1 / c2 encoder geometry (TimeSformer-L/14: D=1024, 24 layers, 16 heads, 256 patches), 4 frames, 1 clip
     "enc_l14": dict(kind="encoder", seed=14, B=1, G=2,
                     cfg=dict(img=224, patch=14, D=1024, L=24, H=16, T=4, **_TXT), stride=(41, 13)),
+    # the headline (c2 / c3) encoder geometry: the same tower at 16 frames (N = 4097 tokens), 1 clip
+    "enc_l14_t16": dict(kind="encoder", seed=16, B=1, G=2,
+                        cfg=dict(img=224, patch=14, D=1024, L=24, H=16, T=16, **_TXT), stride=(163, 13)),
     # full LARGE text tower (12 layers x 768, 12 heads, vocabulary 49408; model/LaviLa.py:141-147) beside a tiny visual tower
     "txt_large": dict(kind="encoder", seed=15, B=1, G=6,
                       cfg=dict(img=56, patch=14, D=128, L=1, H=2, T=3, text_width=768, text_heads=12, text_layers=12,

@@ -155,9 +155,12 @@ def run_reference(case):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true", help="compare live reference with committed fixtures")
+    ap.add_argument("--only", default=None, help="comma-separated case names (default: all)")
     args = ap.parse_args()
     os.makedirs(gc.GOLDEN_DIR, exist_ok=True)
     for name, case in gc.CASES.items():
+        if args.only and name not in args.only.split(","):
+            continue
         res = run_reference(case)
         path = os.path.join(gc.GOLDEN_DIR, name + ".pt")
         if args.check:

@@ -36,7 +36,7 @@ def test_oracle_matches_golden_fixture(name):
 
 
 @pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree only exists in the build container")
-@pytest.mark.parametrize("name", ["enc_tiny", "enc_l14", "dec_tiny_traj", "dec_tiny_notraj", "dec_train_dropout", "boxes", "score", "losses"])
+@pytest.mark.parametrize("name", ["enc_tiny", "enc_l14", "enc_l14_t16", "dec_tiny_traj", "dec_tiny_notraj", "dec_train_dropout", "boxes", "score", "losses"])
 def test_fixture_is_what_the_live_reference_says(name):
     from oracle import make_golden
     live = make_golden.run_reference(gc.CASES[name])
