@@ -9,10 +9,17 @@
 //     O[256 x 64]  = P V       tcgen05.mma 128x64x16, A = P (TMEM), B = V (smem, N-major), D -> TMEM
 // plus the CLS key/value (one extra logit per row, folded in registers).
 //
+// The two 128-row halves of a task are INDEPENDENT chains (S -> max -> exp -> P V -> store) that run half a period
+// apart: while one half's 8 warps are in the exp pass (MUFU), the other half's are in the phases that do not touch the
+// MUFU (waiting for S, row maxima, O read-out, stores).  What keeps them apart is that nothing couples them: Q (per
+// half), K and V have their own full / empty barriers, so a tile is refilled as soon as ITS last reader is done (K right
+// after the second S, Q[h] after half h's output store has left its rows, V after the second P V), and the MMA thread
+// polls both chains instead of waiting on either.
+//
 // Persistent CTA, 24 warps:
-//    0      TMA producer (4-D tensor maps: rows past n are zero-filled / clipped by hardware; the next task's tiles are
-//           in flight into the other smem stage while this one is processed)
-//    1      MMA issuer (one thread);  2  TMEM allocator
+//    0      TMA producer (4-D tensor maps, 128-row boxes: rows past n are zero-filled / clipped by hardware; the next
+//           task's tiles are in flight into the other smem stage while this one is processed)
+//    1      MMA issuer (one thread, polling);  2  TMEM allocator
 //    4-19   softmax + epilogue: TMEM lane r = query row r of a half; the 256 key columns of a row are split between
 //           two threads (column groups A: keys 0..127, B: keys 128..255) that exchange their partial max / sum through
 //           shared memory -- 16 warps keep the MUFU and issue slots busy
@@ -35,19 +42,23 @@ constexpr int ROWS = 256;                 // query / key slots per task
 constexpr int TILE_BYTES = ROWS * 128;    // 32 KB: [256 rows x 64 bf16], SWIZZLE_128B
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int NSTAGE = 2;
+constexpr int NCLS = 4;                     // CLS-vector ring: a slot is rewritten 4 tasks later, long after its readers
+constexpr int HALF_BYTES = TILE_BYTES / 2; // one 128-row box
 constexpr int NTHREADS = 768;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int PART = HD + 2;
 
 struct SmemExtras {
-  __nv_bfloat16 cls_q[NSTAGE][HD];   // q, k, v of the CLS token for (clip, head) of the staged task
-  __nv_bfloat16 cls_k[NSTAGE][HD];
-  __nv_bfloat16 cls_v[NSTAGE][HD];
+  __nv_bfloat16 cls_q[NCLS][HD];     // q, k, v of the CLS token for (clip, head): ring over the last NCLS tasks
+  __nv_bfloat16 cls_k[NCLS][HD];
+  __nv_bfloat16 cls_v[NCLS][HD];
   float scls[NSTAGE][ROWS];          // CLS-key logit of every query row
   float xm[2][2][128];               // [half][column group][row]: partial row max
   float xl[2][2][128];               // partial row sum
   float merge[4][PART];              // CLS-query partials of the four helper warps
-  uint64_t full[NSTAGE], empty[NSTAGE], scls_full[NSTAGE];
+  uint64_t q_full[NSTAGE][2], k_full[NSTAGE], v_full[NSTAGE];      // per tile: Q rows of half h, K (+ CLS vectors), V
+  uint64_t q_empty[NSTAGE][2], k_empty[NSTAGE], v_empty[NSTAGE];
+  uint64_t scls_full[NSTAGE];
   uint64_t s_full[2], p_full[2], o_full[2], t_free[2];
   uint32_t tmem_slot;
 };
@@ -102,8 +113,14 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&ex->full[s], 1);
-      mbar_init(&ex->empty[s], 18);  // MMA commit + 16 epilogue warps (stores have read smem) + helper warps
+      for (int h = 0; h < 2; ++h) {
+        mbar_init(&ex->q_full[s][h], 1);
+        mbar_init(&ex->q_empty[s][h], 9);   // the half's 8 warps (output store has left the rows) + helper warps
+      }
+      mbar_init(&ex->k_full[s], 1);
+      mbar_init(&ex->v_full[s], 1);
+      mbar_init(&ex->k_empty[s], 3);        // commit after each half's S + helper warps
+      mbar_init(&ex->v_empty[s], 3);        // commit after each half's P V + helper warps
       mbar_init(&ex->scls_full[s], 4);
     }
     for (int h = 0; h < 2; ++h) {
@@ -131,62 +148,90 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
-        mbar_wait(&ex->empty[st], ph ^ 1u);
-        trace_ev(p, 0, it, 0);
+        const int cs = it & (NCLS - 1);
         uint8_t* base = smem + st * STAGE_BYTES;
-        mbar_arrive_expect_tx(&ex->full[st], STAGE_BYTES + 3 * HD * 2);
-        tma_load_4d(&tm_in, &ex->full[st], base, h * HD, 0, f, b);                           // Q
-        tma_load_4d(&tm_in, &ex->full[st], base + TILE_BYTES, D + h * HD, 0, f, b);          // K
-        tma_load_4d(&tm_in, &ex->full[st], base + 2 * TILE_BYTES, 2 * D + h * HD, 0, f, b);  // V
+        // tiles in the order their previous contents die: K, Q[0], V, Q[1]
+        mbar_wait(&ex->k_empty[st], ph ^ 1u);
+        trace_ev(p, 0, it, 0);
+        mbar_arrive_expect_tx(&ex->k_full[st], TILE_BYTES + 3 * HD * 2);
+        tma_load_4d(&tm_in, &ex->k_full[st], base + TILE_BYTES, D + h * HD, 0, f, b);
+        tma_load_4d(&tm_in, &ex->k_full[st], base + TILE_BYTES + HALF_BYTES, D + h * HD, 128, f, b);
         const bf16* cls = p.qkv + static_cast<size_t>(b) * N * 3 * D + h * HD;
-        bulk_load_1d(ex->cls_q[st], cls, HD * 2, &ex->full[st]);
-        bulk_load_1d(ex->cls_k[st], cls + D, HD * 2, &ex->full[st]);
-        bulk_load_1d(ex->cls_v[st], cls + 2 * D, HD * 2, &ex->full[st]);
+        bulk_load_1d(ex->cls_q[cs], cls, HD * 2, &ex->k_full[st]);
+        bulk_load_1d(ex->cls_k[cs], cls + D, HD * 2, &ex->k_full[st]);
+        bulk_load_1d(ex->cls_v[cs], cls + 2 * D, HD * 2, &ex->k_full[st]);
+        mbar_wait(&ex->q_empty[st][0], ph ^ 1u);
+        mbar_arrive_expect_tx(&ex->q_full[st][0], HALF_BYTES);
+        tma_load_4d(&tm_in, &ex->q_full[st][0], base, h * HD, 0, f, b);
+        mbar_wait(&ex->v_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&ex->v_full[st], TILE_BYTES);
+        tma_load_4d(&tm_in, &ex->v_full[st], base + 2 * TILE_BYTES, 2 * D + h * HD, 0, f, b);
+        tma_load_4d(&tm_in, &ex->v_full[st], base + 2 * TILE_BYTES + HALF_BYTES, 2 * D + h * HD, 128, f, b);
+        mbar_wait(&ex->q_empty[st][1], ph ^ 1u);
+        mbar_arrive_expect_tx(&ex->q_full[st][1], HALF_BYTES);
+        tma_load_4d(&tm_in, &ex->q_full[st][1], base + HALF_BYTES, h * HD, 128, f, b);
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (one thread)
-    // Both 128-row halves of a task run concurrently on the two TMEM halves; the next task's Q/K/V are already in
-    // flight into the other smem stage.
+    // The two halves are independent chains; each alternates between "S wanted" (its TMEM half is free, Q[h] and K
+    // have landed) and "P V wanted" (its P is in TMEM, V has landed).  The thread polls both with bounded try_waits and
+    // issues whatever is ready, so neither chain ever waits for the other's softmax.  Half 1 starts half a period late
+    // (after half 0's first P V), which puts the chains in anti-phase from the first task on.
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, HD);
-      int it = 0;
-      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;   // parity of the stage barriers
-        const uint32_t tp = it & 1;          // parity of the per-task barriers
-        const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
-        const uint32_t ks = qs + TILE_BYTES, vs = qs + 2 * TILE_BYTES;
-        mbar_wait(&ex->full[st], ph);
-        trace_ev(p, 1, it, 0);
-        tc_fence_after();
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&ex->t_free[hf], tp ^ 1u);   // previous task's O has left these columns
-          tc_fence_after();
-          const uint64_t da = umma_desc_sw128(qs + hf * (128 * 128));
-          const uint64_t db = umma_desc_sw128(ks);
+      int my_tasks = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) ++my_tasks;
+      int it[2] = {0, 0};
+      int stage_of[2] = {0, 0};       // 0: S wanted, 1: P V wanted
+      bool started1 = false;
+      while (it[0] < my_tasks || it[1] < my_tasks) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + hf * 256, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&ex->s_full[hf]);
-          trace_ev(p, 1, it, 1 + hf);
-        }
         for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&ex->p_full[hf], tp);
-          trace_ev(p, 1, it, 3 + 2 * hf);
-          tc_fence_after();
-          const uint64_t dv = umma_desc_sw128_mn(vs);
+          if (it[hf] >= my_tasks) continue;
+          const int u = it[hf];
+          const int st = u & 1;
+          const uint32_t ph = (u >> 1) & 1;   // parity of the stage barriers
+          const uint32_t tp = u & 1;          // parity of the per-task barriers
+          const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
+          const uint32_t ks = qs + TILE_BYTES, vs = qs + 2 * TILE_BYTES;
+          if (stage_of[hf] == 0) {
+            if (hf == 1 && !started1) continue;
+            if (!mbar_try_wait_ns(&ex->t_free[hf], tp ^ 1u, 64)) continue;   // previous task's O has left these columns
+            if (!mbar_try_wait_ns(&ex->q_full[st][hf], ph, 64)) continue;
+            if (!mbar_try_wait_ns(&ex->k_full[st], ph, 64)) continue;
+            if (hf == 0) trace_ev(p, 1, u, 0);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(qs + hf * HALF_BYTES);
+            const uint64_t db = umma_desc_sw128(ks);
 #pragma unroll
-          for (int k = 0; k < ROWS / 16; ++k) {  // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
-            const uint32_t pcol = (k < 8) ? 8 * k : 128 + 8 * (k - 8);
-            umma_bf16_ts(tmem_base + hf * 256 + 192, tmem_base + hf * 256 + pcol, dv + static_cast<uint64_t>(k * 128),
-                         idesc_o, k > 0 ? 1u : 0u);
+            for (int k = 0; k < HD / 16; ++k)
+              umma_bf16(tmem_base + hf * 256, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&ex->s_full[hf]);
+            umma_commit(&ex->k_empty[st]);    // (with the other half's commit and the helpers) K may be refilled
+            trace_ev(p, 1, u, 1 + hf);
+            stage_of[hf] = 1;
+          } else {
+            if (!mbar_try_wait_ns(&ex->p_full[hf], tp, 64)) continue;
+            if (!mbar_try_wait_ns(&ex->v_full[st], ph, 64)) continue;
+            trace_ev(p, 1, u, 3 + 2 * hf);
+            tc_fence_after();
+            const uint64_t dv = umma_desc_sw128_mn(vs);
+#pragma unroll
+            for (int k = 0; k < ROWS / 16; ++k) {  // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
+              const uint32_t pcol = (k < 8) ? 8 * k : 128 + 8 * (k - 8);
+              umma_bf16_ts(tmem_base + hf * 256 + 192, tmem_base + hf * 256 + pcol, dv + static_cast<uint64_t>(k * 128),
+                           idesc_o, k > 0 ? 1u : 0u);
+            }
+            umma_commit(&ex->o_full[hf]);
+            umma_commit(&ex->v_empty[st]);
+            trace_ev(p, 1, u, 4 + 2 * hf);
+            stage_of[hf] = 0;
+            ++it[hf];
+            if (hf == 0) started1 = true;
           }
-          umma_commit(&ex->o_full[hf]);
-          trace_ev(p, 1, it, 4 + 2 * hf);
         }
-        umma_commit(&ex->empty[st]);  // every MMA that read this stage's Q, K, V has retired
       }
     }
   } else if (warp >= 20) {
@@ -202,7 +247,11 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
-      mbar_wait(&ex->full[st], ph);
+      const int cs = it & (NCLS - 1);
+      mbar_wait(&ex->k_full[st], ph);
+      mbar_wait(&ex->q_full[st][0], ph);
+      mbar_wait(&ex->v_full[st], ph);
+      mbar_wait(&ex->q_full[st][1], ph);
       if (ww == 0 && lane == 0) trace_ev(p, 2, it, 0);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
       const uint32_t ks = qs + TILE_BYTES, vs = ks + TILE_BYTES;
@@ -211,8 +260,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       uint32_t kb0[4], kb1[4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        kb0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[st][kk * 16 + 2 * t]) : 0u;
-        kb1[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[st][kk * 16 + 8 + 2 * t]) : 0u;
+        kb0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[cs][kk * 16 + 2 * t]) : 0u;
+        kb1[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_k[cs][kk * 16 + 8 + 2 * t]) : 0u;
       }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {   // 2 x 2 row blocks; 8 fragment loads in flight
@@ -242,8 +291,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       uint32_t qa0[4], qa2[4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        qa0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[st][kk * 16 + 2 * t]) : 0u;
-        qa2[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[st][kk * 16 + 8 + 2 * t]) : 0u;
+        qa0[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[cs][kk * 16 + 2 * t]) : 0u;
+        qa2[kk] = (g == 0) ? *reinterpret_cast<const uint32_t*>(&ex->cls_q[cs][kk * 16 + 8 + 2 * t]) : 0u;
       }
       float m = -INFINITY, l = 0.f;
       float o[8][4];
@@ -355,8 +404,13 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         }
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");  // merge[] reusable; all four warps are done with Q, K and V
-      if (ww == 0 && lane == 0) mbar_arrive(&ex->empty[st]);
-      if (ww == 0 && lane == 0) trace_ev(p, 2, it, 2);
+      if (ww == 0 && lane == 0) {
+        mbar_arrive(&ex->k_empty[st]);
+        mbar_arrive(&ex->v_empty[st]);
+        mbar_arrive(&ex->q_empty[st][0]);
+        mbar_arrive(&ex->q_empty[st][1]);
+        trace_ev(p, 2, it, 2);
+      }
     }
   } else if (warp >= 4) {
     // ================================================================== softmax + epilogue (two threads per row)
@@ -384,7 +438,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t tp = u & 1;
       const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
-      mbar_wait(&ex->full[st], ph);        // TMA-written cls_v visible to this thread
+      const int cs = u & (NCLS - 1);
+      mbar_wait(&ex->k_full[st], ph);      // TMA-written cls_v visible to this thread
       mbar_wait(&ex->scls_full[st], ph);
      {
       const float s_cls = ex->scls[st][r];
@@ -416,7 +471,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       if (tr) trace_ev(p, 3 + jh, u, 1);
       if (release_st >= 0 && lane == 0) {
         tma_store_wait_read<0>();
-        mbar_arrive(&ex->empty[release_st]);
+        mbar_arrive(&ex->q_empty[release_st][hf]);
       }
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
@@ -485,7 +540,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t stg = qs + static_cast<uint32_t>((jh * 128 + wq * 32) * 128 + cg * 2048);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[st][cg * 32 + c * 8]);
+        const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[cs][cg * 32 + c * 8]);
         const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z), v3 = unpack_bf16x2(vv.w);
         const uint32_t w0 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 0]), inv, pc * v0.x),
                                         fmaf(__uint_as_float(o[c * 8 + 1]), inv, pc * v0.y));
@@ -570,7 +625,7 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
              "attn_space_tc: 16-byte alignment");
   const int D = H * HD, N = 1 + T * n;
   CUtensorMap tm_in, tm_out;
-  int rc = make_map4d(&tm_in, qkv + static_cast<size_t>(3) * D, 3 * D, n, T, B, N, 64, ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_map4d(&tm_in, qkv + static_cast<size_t>(3) * D, 3 * D, n, T, B, N, 64, ROWS / 2, CU_TENSOR_MAP_SWIZZLE_128B);  // 128-row boxes
   if (rc) return rc;
   rc = make_map4d(&tm_out, out + D, D, n, T, B, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;

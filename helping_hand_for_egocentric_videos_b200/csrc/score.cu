@@ -3,9 +3,17 @@
 // sim_matrix: fused L2-normalise + similarity.  A 32x64 output tile streams the embedding dimension once and
 // accumulates the dot products together with the squared row norms of both operands, so the embeddings are read
 // once and never written back normalised:  out = a.b / (max(|a|, eps) * max(|b|, eps)).
+// Large problems (EPIC-MIR: 9728 x 9728 x 256, the c4 EgoNCE matrix) run on the tcgen05 GEMM instead: rows are normalised
+// in fp32 and split into a bf16 (hi, lo) pair by split_normalize_kernel, and out = [hi hi lo lo] . [hi lo hi lo]^T is one
+// bf16 GEMM with K = 4 d and fp32 accumulation -- every product of two bf16 values is exact in fp32, the pair carries
+// 16 mantissa bits, so the result stays within ~2e-6 of the fp32 statement (test: 1e-5 against fp64) while the kernel
+// becomes output-write bound.
 // row_reduce: one warp per row -- argmax (first maximum, like torch.argmax), softmax or log_softmax of scale * x.
 #include "hh_internal.h"
 #include "hh_ptx.cuh"
+#include "engine.h"
+
+#include <cstdlib>
 
 namespace hh {
 
@@ -65,6 +73,30 @@ sim_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
   }
 }
 
+// warp per row: y = x / max(|x|, eps); out row = [hi hi lo lo] (order 0) or [hi lo hi lo] (order 1), hi = bf16(y),
+// lo = bf16(y - hi)
+__global__ void __launch_bounds__(256)
+split_normalize_kernel(const float* __restrict__ x, bf16* __restrict__ out, int rows, int d, float eps, int order) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<size_t>(row) * d;
+  float sq = 0.f;
+  for (int c = lane; c < d; c += 32) sq = fmaf(xr[c], xr[c], sq);
+  sq = warp_sum(sq);
+  const float inv = 1.0f / fmaxf(sqrtf(sq), eps);
+  bf16* o = out + static_cast<size_t>(row) * 4 * d;
+  for (int c = lane; c < d; c += 32) {
+    const float y = xr[c] * inv;
+    const bf16 hi = __float2bfloat16_rn(y);
+    const bf16 lo = __float2bfloat16_rn(y - __bfloat162float(hi));
+    o[c] = hi;
+    o[d + c] = order ? lo : hi;
+    o[2 * d + c] = order ? hi : lo;
+    o[3 * d + c] = lo;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 row_reduce_kernel(const float* __restrict__ x, int rows, int cols, float scale, int mode, void* __restrict__ out) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -108,8 +140,25 @@ row_reduce_kernel(const float* __restrict__ x, int rows, int cols, float scale, 
 
 }  // namespace
 
+// operand workspace of the tensor-core path: grow-only, one per process (the C ABI is not re-entrant per device)
+static DevBuf g_sim_ws;
+
 int sim_matrix(const float* a, const float* b, float* out, int Na, int Nb, int d, float eps, cudaStream_t stream) {
   HH_REQUIRE(Na > 0 && Nb > 0 && d > 0, "sim_matrix: empty problem");
+  static const bool tc_ok = std::getenv("HH_SIM_SIMT") == nullptr;
+  if (tc_ok && Na >= 128 && Nb >= 128 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    const size_t abytes = (static_cast<size_t>(Na) * 4 * d * 2 + 255) & ~size_t(255);
+    const size_t bbytes = static_cast<size_t>(Nb) * 4 * d * 2;
+    int rc = g_sim_ws.reserve(abytes + bbytes);
+    if (rc) return rc;
+    bf16* a4 = static_cast<bf16*>(g_sim_ws.ptr);
+    bf16* b4 = reinterpret_cast<bf16*>(static_cast<uint8_t*>(g_sim_ws.ptr) + abytes);
+    split_normalize_kernel<<<(Na + 7) / 8, 256, 0, stream>>>(a, a4, Na, d, eps, 0);
+    HH_CHECK_LAUNCH("split_normalize_kernel");
+    split_normalize_kernel<<<(Nb + 7) / 8, 256, 0, stream>>>(b, b4, Nb, d, eps, 1);
+    HH_CHECK_LAUNCH("split_normalize_kernel");
+    return gemm_bf16(a4, 4 * d, b4, 4 * d, out, Nb, nullptr, nullptr, 0, Na, Nb, 4 * d, EPI_BIAS_F32, stream);
+  }
   dim3 grid((Nb + SBN - 1) / SBN, (Na + SBM - 1) / SBM);
   HH_REQUIRE(grid.y < 65536, "sim_matrix: too many rows for one launch");
   sim_kernel<<<grid, 256, 0, stream>>>(a, b, out, Na, Nb, d, eps);

@@ -252,7 +252,7 @@ def text_forward(tokens: Tensor, sd, heads: int) -> Tuple[Tensor, Tensor]:
     x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
     G, Lc, W = x.shape
     hd = W // heads
-    causal = torch.full((Lc, Lc), float("-inf")).triu_(1)
+    causal = torch.full((Lc, Lc), float("-inf"), device=x.device).triu_(1)
     i = 0
     while ("transformer.resblocks.%d.ln_1.weight" % i) in sd:
         p = "transformer.resblocks.%d." % i
