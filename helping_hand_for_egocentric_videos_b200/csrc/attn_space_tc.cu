@@ -58,7 +58,7 @@ struct SmemExtras {
   float merge[4][PART];              // CLS-query partials of the four helper warps
   uint64_t q_full[NSTAGE][2], k_full[NSTAGE], v_full[NSTAGE];      // per tile: Q rows of half h, K (+ CLS vectors), V
   uint64_t q_empty[NSTAGE][2], k_empty[NSTAGE], v_empty[NSTAGE];
-  uint64_t scls_full[NSTAGE];
+  uint64_t scls_full[NSTAGE][2];     // CLS-key logits of half h's rows (helper warps 2h, 2h + 1)
   uint64_t s_full[2], p_full[2], o_full[2], t_free[2];
   uint32_t tmem_slot;
 };
@@ -121,7 +121,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       mbar_init(&ex->v_full[s], 1);
       mbar_init(&ex->k_empty[s], 3);        // commit after each half's S + helper warps
       mbar_init(&ex->v_empty[s], 3);        // commit after each half's P V + helper warps
-      mbar_init(&ex->scls_full[s], 4);
+      mbar_init(&ex->scls_full[s][0], 2);
+      mbar_init(&ex->scls_full[s][1], 2);
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&ex->s_full[h], 1);
@@ -248,10 +249,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t ph = (it >> 1) & 1;
       const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
       const int cs = it & (NCLS - 1);
+      // this warp's 64 query rows belong to half ww / 2: their CLS-key logits only need that half of Q (and k_cls)
       mbar_wait(&ex->k_full[st], ph);
-      mbar_wait(&ex->q_full[st][0], ph);
-      mbar_wait(&ex->v_full[st], ph);
-      mbar_wait(&ex->q_full[st][1], ph);
+      mbar_wait(&ex->q_full[st][ww >> 1], ph);
       if (ww == 0 && lane == 0) trace_ev(p, 2, it, 0);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
       const uint32_t ks = qs + TILE_BYTES, vs = ks + TILE_BYTES;
@@ -284,8 +284,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ex->scls_full[st]);
+      if (lane == 0) mbar_arrive(&ex->scls_full[st][ww >> 1]);
       if (ww == 0 && lane == 0) trace_ev(p, 2, it, 1);
+      mbar_wait(&ex->v_full[st], ph);   // part (2) reads K and V
 
       // ---- (2) CLS query vs this warp's 64 keys: online softmax over 2 blocks of 32 keys, row 0 of the A block live
       uint32_t qa0[4], qa2[4];
@@ -440,7 +441,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
       const int cs = u & (NCLS - 1);
       mbar_wait(&ex->k_full[st], ph);      // TMA-written cls_v visible to this thread
-      mbar_wait(&ex->scls_full[st], ph);
+      mbar_wait(&ex->scls_full[st][hf], ph);
      {
       const float s_cls = ex->scls[st][r];
       const bool tr = (cg == 0 && wq == 0 && lane == 0);
