@@ -25,6 +25,19 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and d["gpu_launches"] == 0
 
 
+def test_reference_arm_other_configuration():
+    """--config selects another BASELINE.json configuration through the same contract (c1: 4 frames, nq = 4)."""
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "clips/sec (4f x 224^2, nq=4)" and d["config"]["name"] == "c1"
+    assert "configs[1]" in d["config"]["workload"] and d["value"] > 0
+
+
 def test_reference_arm_is_silent_on_other_ranks():
     """Under torchrun only rank 0 runs and prints; the other ranks exit 0 without work."""
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
