@@ -323,6 +323,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const int m_blk = CLUSTER ? 2 * mp + cta_rank : mp;
 #pragma unroll 1
           for (int u = 0; u < BLOCK_N / 32; ++u) {
+#ifdef HH_GEMM_RES_NOLOAD   // experiment: the producer epilogue without its residual loads (results are wrong)
+            continue;
+#endif
             mbar_wait(&my_empty[slot], phase ^ 1u);
             mbar_arrive_expect_tx(&my_full[slot], 4096);
 #ifdef HH_GEMM_RES_HINTS
@@ -440,7 +443,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t slot = static_cast<uint32_t>(res_slot);
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(u * 32), r);   // in flight while the residual box is awaited
+#ifndef HH_GEMM_RES_NOLOAD
           { TR_T0(); mbar_wait(&my_res_full[slot], res_phase); TR_ADD(5); }
+#endif
           const uint32_t rrow = res_ring + slot * 4096u + static_cast<uint32_t>(lane * 128);
           const uint32_t zrow = zring + static_cast<uint32_t>(epi_slot * 4096 + lane * 128);
           tmem_ld_wait();

@@ -55,6 +55,7 @@ add("proj_res_nowb", lambda: ops.gemm_bf16_res_stats(a1, w_proj, b_proj, x, writ
 add("proj_res_wb", lambda: ops.gemm_bf16_res_stats(a1, w_proj, b_proj, x, writeback=True), 2.0 * M * D * D, 8.0 * M * D)
 add("fc2_plain", lambda: ops.gemm_bf16(h, w_fc2, b_fc2, out=out_d), 2.0 * M * D * Hd, 0)
 add("fc2_res_wb", lambda: ops.gemm_bf16_res_stats(h, w_fc2, b_fc2, x, writeback=True), 2.0 * M * D * Hd, 8.0 * M * D)
+add("fc2_res_nowb", lambda: ops.gemm_bf16_res_stats(h, w_fc2, b_fc2, x, writeback=False), 2.0 * M * D * Hd, 4.0 * M * D)
 add("qkv_plain", lambda: ops.gemm_bf16(a1, w_qkv, b_qkv, out=out_3d), 2.0 * M * 3 * D * D, 0)
 add("qkv_ln", lambda: ops.gemm_bf16_ln(a1, wq_f, bq_f, cs_q, stats, 1e-6), 2.0 * M * 3 * D * D, 0)
 add("fc1_plain", lambda: ops.gemm_bf16(a1, w_fc1, b_fc1, epilogue=1, out=out_h), 2.0 * M * Hd * D, 0)
