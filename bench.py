@@ -718,9 +718,22 @@ def run_forward(ctx):
     g_fl = sum(gemm_flops[k] * prof[k][1] for k in gemm_flops if k in prof)
     gemm_tflops = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     per_class = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    # algorithmic bytes per launch of each GEMM class (A + W + output in bf16; with the LayerNorm folded in, the proj / fc2
+    # launches also carry the fp32 residual stream: proj = time-proj (x read) and space-proj (x read + written) alternating,
+    # fc2 = x read + written): the producers are co-bound by HBM, so both roofline fractions are reported per class
+    fused_ln = os.environ.get("HH_LN_UNFUSED", "0") in ("", "0")
+    D_, H_ = 1024, 4096
+    res_extra = {"gemm_proj": 6.0 * M * D_, "gemm_fc2": 8.0 * M * D_} if fused_ln else {}
+    gemm_bytes = {"gemm_qkv": 2.0 * (M * D_ + 3 * D_ * D_ + M * 3 * D_), "gemm_proj": 2.0 * (M * D_ + D_ * D_ + M * D_),
+                  "gemm_fc1": 2.0 * (M * D_ + H_ * D_ + M * H_), "gemm_fc2": 2.0 * (M * H_ + D_ * H_ + M * D_)}
     for k in gemm_flops:
         if k in prof and prof[k][0] > 0:
-            per_class[k]["tflops"] = gemm_flops[k] * prof[k][1] / (prof[k][0] * 1e-3) / 1e12
+            sec = prof[k][0] * 1e-3 / prof[k][1]
+            per_class[k]["tflops"] = gemm_flops[k] / sec / 1e12
+            per_class[k]["frac_of_sustained_bf16"] = gemm_flops[k] / sec / 1e12 / peaks["sustained"]
+            nbytes = gemm_bytes[k] + res_extra.get(k, 0.0)
+            per_class[k]["algorithmic_GB_per_launch"] = nbytes / 1e9
+            per_class[k]["frac_of_hbm"] = nbytes / sec / 1e9 / peaks["hbm"]
     # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture at these very shapes
     # (profiles/*_gemm_traffic.json, newest round first), averaged over the launches of one step like `achieved`.
     traffic, traffic_detail = None, None
@@ -753,7 +766,13 @@ def run_forward(ctx):
                      "achieved": gemm_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["sustained"], "peak_source": peaks["source"] + " sustained bf16",
                      "share_of_step": g_ms / args.steps / ms_step if ms_step > 0 else None, "traffic": traffic,
-                     "traffic_detail": traffic_detail},
+                     "traffic_detail": traffic_detail,
+                     "note": ("LayerNorm and the residual adds run INSIDE these launches (norm1/2/3 folded into the qkv / fc1 "
+                              "epilogues, fp32 residual stream read / rewritten by the proj / fc2 epilogues): `achieved` counts "
+                              "only the 2MNK flops of launches that also move the 20 B per element per layer of the residual "
+                              "stream; per-class tensor and HBM fractions are in config.kernel_ms_per_step "
+                              "(HH_LN_UNFUSED=1 gives the round-1 split: GEMMs at ~0.97 + 30 ms of LayerNorm kernels, a 3 % "
+                              "slower step)") if fused_ln else None},
         "clocks": clocks, "gpu_launches": launches_step * args.steps,
         "rank_ms_per_step": rank_spread(per_rank, args.steps),
     }
