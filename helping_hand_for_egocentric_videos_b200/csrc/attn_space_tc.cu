@@ -20,13 +20,14 @@
 //    0      TMA producer (4-D tensor maps, 128-row boxes: rows past n are zero-filled / clipped by hardware; the next
 //           task's tiles are in flight into the other smem stage while this one is processed)
 //    1      MMA issuer (one thread, polling);  2  TMEM allocator
-//    4-19   softmax + epilogue: TMEM lane r = query row r of a half; the 256 key columns of a row are split between
-//           two threads (column groups A: keys 0..127, B: keys 128..255) that exchange their partial max / sum through
-//           shared memory -- 16 warps keep the MUFU and issue slots busy
-//    20-23  legacy-MMA helpers (highest warp ids = highest issue priority, they gate the softmax warps): the CLS-key
+//    4-11   softmax + epilogue: ONE thread per query row (TMEM lane r = row r of a half, all 256 key columns), 4 warps per
+//           half.  512 threads leave 128 registers per thread: the next 32-column chunk's tcgen05.ld is in flight under
+//           the current chunk's arithmetic in both passes, and no cross-thread max / sum exchange (named barriers, shared
+//           memory round trips) is left in a half's chain
+//    12-15  legacy-MMA helpers (highest warp ids = highest issue priority, they gate the softmax warps): the CLS-key
 //           logit of every row (q_r . k_cls) and the CLS *query*'s partial softmax over this frame's keys (merged
 //           across frames by attn_cls_merge)
-// TMEM (512 columns), half h owns [256h, 256h+256): S; then P_A in [0,64), P_B in [128,192), O in [192,256).
+// TMEM (512 columns), half h owns [256h, 256h+256): S; then P (bf16 pairs) in [0,128), O in [192,256).
 #include <cstdio>
 #include <cstdlib>
 
@@ -44,7 +45,7 @@ constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int NCLS = 4;                     // CLS-vector ring: a slot is rewritten 4 tasks later, long after its readers
 constexpr int HALF_BYTES = TILE_BYTES / 2; // one 128-row box
-constexpr int NTHREADS = 768;
+constexpr int NTHREADS = 512;                // 16 warps: 128 registers per thread
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int PART = HD + 2;
 
@@ -53,8 +54,6 @@ struct SmemExtras {
   __nv_bfloat16 cls_k[NCLS][HD];
   __nv_bfloat16 cls_v[NCLS][HD];
   float scls[NSTAGE][ROWS];          // CLS-key logit of every query row
-  float xm[2][2][128];               // [half][column group][row]: partial row max
-  float xl[2][2][128];               // partial row sum
   float merge[4][PART];              // CLS-query partials of the four helper warps
   uint64_t q_full[NSTAGE][2], k_full[NSTAGE], v_full[NSTAGE];      // per tile: Q rows of half h, K (+ CLS vectors), V
   uint64_t q_empty[NSTAGE][2], k_empty[NSTAGE], v_empty[NSTAGE];
@@ -115,7 +114,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     for (int s = 0; s < NSTAGE; ++s) {
       for (int h = 0; h < 2; ++h) {
         mbar_init(&ex->q_full[s][h], 1);
-        mbar_init(&ex->q_empty[s][h], 9);   // the half's 8 warps (output store has left the rows) + helper warps
+        mbar_init(&ex->q_empty[s][h], 5);   // the half's 4 warps (output store has left the rows) + helper warps
       }
       mbar_init(&ex->k_full[s], 1);
       mbar_init(&ex->v_full[s], 1);
@@ -126,9 +125,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&ex->s_full[h], 1);
-      mbar_init(&ex->p_full[h], 8);
+      mbar_init(&ex->p_full[h], 4);
       mbar_init(&ex->o_full[h], 1);
-      mbar_init(&ex->t_free[h], 8);
+      mbar_init(&ex->t_free[h], 4);
     }
     fence_mbar_init();
   }
@@ -221,7 +220,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             const uint64_t dv = umma_desc_sw128_mn(vs);
 #pragma unroll
             for (int k = 0; k < ROWS / 16; ++k) {  // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
-              const uint32_t pcol = (k < 8) ? 8 * k : 128 + 8 * (k - 8);
+              const uint32_t pcol = 8 * k;   // P: 256 keys as 128 packed columns from column 0 of the half
               umma_bf16_ts(tmem_base + hf * 256 + 192, tmem_base + hf * 256 + pcol, dv + static_cast<uint64_t>(k * 128),
                            idesc_o, k > 0 ? 1u : 0u);
             }
@@ -235,12 +234,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         }
       }
     }
-  } else if (warp >= 20) {
+  } else if (warp >= 12) {
     // ================================================================== helpers on the legacy tensor-core path
     // 4 warps; every warp takes 4 of the 16 query-row blocks for the CLS-key logits and 64 of the 256 keys for the
     // CLS-query partial.  Fragment loads are issued in batches ahead of the MMAs that use them (one warp has no other
     // warp to hide its ldmatrix -> mma latency behind).
-    const int ww = warp - 20;
+    const int ww = warp - 12;
     const int g = lane >> 2, t = lane & 3;
     const int mi = lane >> 3, lr = lane & 7;
     int it = 0;
@@ -414,22 +413,19 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ================================================================== softmax + epilogue (two threads per row)
-    const int sw = warp - 4;                  // 0..15
-    const int hf = (sw >> 2) & 1;             // 0: rows 0..127, 1: rows 128..255 (TMEM half hf)
-    const int cg = sw >> 3;                   // column group: 0 = keys 0..127, 1 = keys 128..255
+    // ================================================================== softmax + epilogue (one thread per row)
+    const int sw = warp - 4;                  // 0..7
+    const int hf = sw >> 2;                   // 0: rows 0..127, 1: rows 128..255 (TMEM half hf)
     const int wq = warp & 3;                  // TMEM lane quarter of this warp
     const int rl = wq * 32 + lane;            // row within the half
     const int r = hf * 128 + rl;              // row within the task
     const int jh = hf;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(hf * 256);
-    const uint32_t s_col = t_lane + cg * 128;               // this thread's 128 S columns
-    const uint32_t p_col = t_lane + (cg ? 128 : 0);         // its 64 P columns
-    const uint32_t o_col = t_lane + 192 + cg * 32;          // its 32 O columns (dims cg*32 ..)
-    const int key_base = cg * 128;
-    const int bar_id = 3 + hf;                              // named barrier of the 256 threads of this half
-    const int nvalid = min(128, max(0, p.n - key_base));    // valid keys in this thread's column group
-    const int nch = (nvalid + 31) >> 5;
+    const uint32_t s_col = t_lane;            // this row's 256 S columns
+    const uint32_t p_col = t_lane;            // its 128 P columns (written behind the S columns already consumed)
+    const uint32_t o_col = t_lane + 192;      // its 64 O columns
+    const int nvalid = min(ROWS, p.n);        // valid keys
+    const int nch = (nvalid + 31) >> 5;       // 32-key chunks that hold valid keys (1..8)
     int u = 0;
     int release_st = -1;   // stage whose output store may still be reading its staging rows: released one task later,
                            // after the next task's first pass, instead of stalling the epilogue on the bulk-store read
@@ -442,33 +438,40 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const int cs = u & (NCLS - 1);
       mbar_wait(&ex->k_full[st], ph);      // TMA-written cls_v visible to this thread
       mbar_wait(&ex->scls_full[st][hf], ph);
-     {
       const float s_cls = ex->scls[st][r];
-      const bool tr = (cg == 0 && wq == 0 && lane == 0);
+      const bool tr = (wq == 0 && lane == 0);
       mbar_wait(&ex->s_full[hf], tp);
       if (tr) trace_ev(p, 3 + jh, u, 0);
       tc_fence_after();
 
-      // ---- pass 1: partial row maximum over this thread's keys
+      uint32_t va[32], vb[32];
+      // ---- pass 1: row maximum; chunk c + 1 is being loaded from TMEM while chunk c is folded
       float mx = s_cls;
+      {
+        auto fold = [&](const uint32_t(&v)[32], int c) {
+          if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+              asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        };
+        tmem_ld_32x32b_x32(s_col, va);
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(s_col + c * 32, v);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= nvalid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2)
-            asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32b_x32(s_col + (c + 1) * 32, vb);
+          fold(va, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld_32x32b_x32(s_col + (c + 2) * 32, va);
+            fold(vb, c + 1);
+          }
         }
       }
-      ex->xm[hf][cg][rl] = mx;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, ex->xm[hf][cg ^ 1][rl]);
       if (tr) trace_ev(p, 3 + jh, u, 1);
       if (release_st >= 0 && lane == 0) {
         tma_store_wait_read<0>();
@@ -477,95 +480,101 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
 
-      // ---- pass 2: P = exp2(S - max) as bf16 pairs into this group's P columns (16 columns per 32 keys)
+      // ---- pass 2: P = exp2(S - max) as bf16 pairs (16 columns per 32 keys), the same double buffering.  P chunk c
+      // overwrites S columns 16c .. 16c + 15, which belong to S chunk c / 2 <= c: already in registers.
       float2 l2 = make_float2(0.f, 0.f);
       {
         const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        auto emit = [&](const uint32_t(&v)[32], int c) {
           uint32_t w[16];
-          if (c < nch) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(s_col + c * 32, v);
-            tmem_ld_wait();
-            if (c * 32 + 32 <= nvalid) {   // full chunk: no per-element masking code at all
+          if (c * 32 + 32 <= nvalid) {     // full chunk: no per-element masking code at all
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-                const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
-                l2 = __fadd2_rn(l2, e);
-                w[j >> 1] = pack_bf16x2(e.x, e.y);
-              }
-            } else {                       // ragged last chunk (n = 196)
+            for (int j = 0; j < 32; j += 2) {
+              const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
+              const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+              l2 = __fadd2_rn(l2, e);
+              w[j >> 1] = pack_bf16x2(e.x, e.y);
+            }
+          } else if (c < nch) {            // ragged last chunk (n = 196)
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-                float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
-                if (c * 32 + j >= nvalid) e.x = 0.f;
-                if (c * 32 + j + 1 >= nvalid) e.y = 0.f;
-                l2 = __fadd2_rn(l2, e);
-                w[j >> 1] = pack_bf16x2(e.x, e.y);
-              }
+            for (int j = 0; j < 32; j += 2) {
+              const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
+              float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+              if (c * 32 + j >= nvalid) e.x = 0.f;
+              if (c * 32 + j + 1 >= nvalid) e.y = 0.f;
+              l2 = __fadd2_rn(l2, e);
+              w[j >> 1] = pack_bf16x2(e.x, e.y);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = 0u;
           }
           tmem_st_32x32b_x16(p_col + c * 16, w);
+        };
+        tmem_ld_32x32b_x32(s_col, va);
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          if (c < nch) tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32b_x32(s_col + (c + 1) * 32, vb);
+          emit(va, c);
+          if (c + 1 < nch) tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld_32x32b_x32(s_col + (c + 2) * 32, va);
+          emit(vb, c + 1);
         }
       }
-      ex->xl[hf][cg][rl] = l2.x + l2.y;
+      const float l = l2.x + l2.y + p_cls;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->p_full[hf]);
       if (tr) trace_ev(p, 3 + jh, u, 2);
 
-      // ---- O = P V is in TMEM columns [192, 256) of this half; this thread takes 32 of the 64 output dims
+      // ---- O = P V is in TMEM columns [192, 256) of this half: all 64 output dims of this row
       mbar_wait(&ex->o_full[hf], tp);
       if (tr) trace_ev(p, 3 + jh, u, 3);
       tc_fence_after();
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(o_col, o);
+      tmem_ld_32x32b_x32(o_col, va);
+      tmem_ld_32x32b_x32(o_col + 32, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->t_free[hf]);   // the next task's S may overwrite this half
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // both groups' xl are visible
-      const float l = ex->xl[hf][0][rl] + ex->xl[hf][1][rl] + p_cls;
 
-      // ---- normalise (+ CLS value), stage the 32 bf16 values (64 B) of this row, bulk-store a 32-row x 64-B box
+      // ---- normalise (+ CLS value), stage the 64 bf16 values (128 B) of this row, bulk-store a 32-row x 128-B box
       const float inv = 1.f / l;
       const float pc = p_cls * inv;
-      // staging: the 4 KB of the (consumed) Q tile that belong to these 32 rows, 2 KB per column group, SWIZZLE_64B
-      const uint32_t stg = qs + static_cast<uint32_t>((jh * 128 + wq * 32) * 128 + cg * 2048);
+      // staging: the 4 KB of the (consumed) Q tile that belong to these 32 rows, SWIZZLE_128B
+      const uint32_t stg = qs + static_cast<uint32_t>((jh * 128 + wq * 32) * 128);
+      auto stage = [&](const uint32_t(&o)[32], int half32) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[cs][cg * 32 + c * 8]);
-        const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z), v3 = unpack_bf16x2(vv.w);
-        const uint32_t w0 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 0]), inv, pc * v0.x),
-                                        fmaf(__uint_as_float(o[c * 8 + 1]), inv, pc * v0.y));
-        const uint32_t w1 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 2]), inv, pc * v1.x),
-                                        fmaf(__uint_as_float(o[c * 8 + 3]), inv, pc * v1.y));
-        const uint32_t w2 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 4]), inv, pc * v2.x),
-                                        fmaf(__uint_as_float(o[c * 8 + 5]), inv, pc * v2.y));
-        const uint32_t w3 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 6]), inv, pc * v3.x),
-                                        fmaf(__uint_as_float(o[c * 8 + 7]), inv, pc * v3.y));
-        st_shared_v4(stg + static_cast<uint32_t>(lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)), w0, w1, w2, w3);
-      }
+        for (int c = 0; c < 4; ++c) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[cs][half32 * 32 + c * 8]);
+          const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z), v3 = unpack_bf16x2(vv.w);
+          const uint32_t w0 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 0]), inv, pc * v0.x),
+                                          fmaf(__uint_as_float(o[c * 8 + 1]), inv, pc * v0.y));
+          const uint32_t w1 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 2]), inv, pc * v1.x),
+                                          fmaf(__uint_as_float(o[c * 8 + 3]), inv, pc * v1.y));
+          const uint32_t w2 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 4]), inv, pc * v2.x),
+                                          fmaf(__uint_as_float(o[c * 8 + 5]), inv, pc * v2.y));
+          const uint32_t w3 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 6]), inv, pc * v3.x),
+                                          fmaf(__uint_as_float(o[c * 8 + 7]), inv, pc * v3.y));
+          st_shared_v4(sw128(stg, lane, half32 * 4 + c), w0, w1, w2, w3);
+        }
+      };
+      stage(va, 0);
+      stage(vb, 1);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         const int row0 = jh * 128 + wq * 32;
         if (row0 < p.n) {
-          tma_store_4d(&tm_out, stg, h * HD + cg * 32, row0, f, b);
+          tma_store_4d(&tm_out, stg, h * HD, row0, f, b);
           tma_store_commit();
         }
       }
       release_st = st;
       __syncwarp();
       if (tr) trace_ev(p, 3 + jh, u, 4);
-     }
     }
     if (lane == 0) tma_store_wait_read<0>();   // shared memory stays valid until the last store has read it
   }
@@ -628,7 +637,7 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
   CUtensorMap tm_in, tm_out;
   int rc = make_map4d(&tm_in, qkv + static_cast<size_t>(3) * D, 3 * D, n, T, B, N, 64, ROWS / 2, CU_TENSOR_MAP_SWIZZLE_128B);  // 128-row boxes
   if (rc) return rc;
-  rc = make_map4d(&tm_out, out + D, D, n, T, B, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = make_map4d(&tm_out, out + D, D, n, T, B, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
