@@ -59,6 +59,7 @@ struct SmemExtras {
   uint64_t q_empty[NSTAGE][2], k_empty[NSTAGE], v_empty[NSTAGE];
   uint64_t scls_full[NSTAGE][2];     // CLS-key logits of half h's rows (helper warps 2h, 2h + 1)
   uint64_t s_full[2], p_full[2], o_full[2], t_free[2];
+  uint64_t x_done[2][4];             // exp pass of half h, TMEM lane quarter q finished (the turn passes to the other half)
   uint32_t tmem_slot;
 };
 constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + static_cast<int>(sizeof(SmemExtras)) + 64;
@@ -94,6 +95,30 @@ __device__ __forceinline__ uint32_t sw128(uint32_t tile, int row, int chunk) {
   return tile + static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// 2^x for two x <= 0 on the FMA / ALU pipes instead of the MUFU: x = n + f with n = round(x), f in [-0.5, 0.5] (magic-number
+// add), 2^f as a degree-3 polynomial (relative error 7.5e-5, well inside the bf16 rounding of P), n added into the
+// exponent field.  Clamped at -125: 2^-125 is nothing next to a row sum >= 1.
+#ifndef HH_ATTN_EMU
+#define HH_ATTN_EMU 1       // pairs out of every 4 that take this path in the exp pass (0 = all on the MUFU)
+#endif
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+  const float MAGIC = 12582912.f;   // 1.5 * 2^23
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 xf = __fadd2_rn(x, make_float2(MAGIC, MAGIC));
+  const float2 fl = __fadd2_rn(xf, make_float2(-MAGIC, -MAGIC));
+  const float2 f = __fadd2_rn(x, make_float2(-fl.x, -fl.y));
+  const float c0 = 0.999928074f, c1 = 0.693260986f, c2 = 0.242611122f, c3 = 0.055171667f;
+  float2 q = __ffma2_rn(f, make_float2(c3, c3), make_float2(c2, c2));
+  q = __ffma2_rn(q, f, make_float2(c1, c1));
+  q = __ffma2_rn(q, f, make_float2(c0, c0));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(xf.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(xf.y) << 23)));
+}
+
+// kFull: n == 256 exactly (the L/14 geometry): no ragged-chunk code in the softmax loops (half the code bytes of the hot
+// loop, compile-time trip counts).
+template <bool kFull>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                      const TcArgs p) {
@@ -128,6 +153,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       mbar_init(&ex->p_full[h], 4);
       mbar_init(&ex->o_full[h], 1);
       mbar_init(&ex->t_free[h], 4);
+      for (int q = 0; q < 4; ++q) mbar_init(&ex->x_done[h][q], 1);
     }
     fence_mbar_init();
   }
@@ -139,6 +165,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ex->tmem_slot;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {   // SM clock of the run: (clock64, globaltimer) pairs
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[TR_ROLES * TR_TASKS * TR_EVENTS + 0] = t;
+    p.trace[TR_ROLES * TR_TASKS * TR_EVENTS + 1] = static_cast<unsigned long long>(clock64());
+  }
 
   if (warp == 0) {
     // ================================================================== TMA producer
@@ -255,6 +287,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
       const uint32_t ks = qs + TILE_BYTES, vs = ks + TILE_BYTES;
 
+#ifndef HH_ATTN_NOHELP
       // ---- (1) CLS-key logit of every query row: S_cls = Q . k_cls, as m16n8k16 with k_cls in column 0 of B
       uint32_t kb0[4], kb1[4];
 #pragma unroll
@@ -282,10 +315,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
         }
       }
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->scls_full[st][ww >> 1]);
       if (ww == 0 && lane == 0) trace_ev(p, 2, it, 1);
       mbar_wait(&ex->v_full[st], ph);   // part (2) reads K and V
+#ifndef HH_ATTN_NOHELP
 
       // ---- (2) CLS query vs this warp's 64 keys: online softmax over 2 blocks of 32 keys, row 0 of the A block live
       uint32_t qa0[4], qa2[4];
@@ -403,6 +438,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           }
         }
       }
+#endif
       asm volatile("bar.sync 2, 128;" ::: "memory");  // merge[] reusable; all four warps are done with Q, K and V
       if (ww == 0 && lane == 0) {
         mbar_arrive(&ex->k_empty[st]);
@@ -424,8 +460,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     const uint32_t s_col = t_lane;            // this row's 256 S columns
     const uint32_t p_col = t_lane;            // its 128 P columns (written behind the S columns already consumed)
     const uint32_t o_col = t_lane + 192;      // its 64 O columns
-    const int nvalid = min(ROWS, p.n);        // valid keys
-    const int nch = (nvalid + 31) >> 5;       // 32-key chunks that hold valid keys (1..8)
+    const int nvalid = kFull ? ROWS : min(ROWS, p.n);        // valid keys
+    const int nch = kFull ? 8 : ((nvalid + 31) >> 5);        // 32-key chunks that hold valid keys (1..8)
     int u = 0;
     int release_st = -1;   // stage whose output store may still be reading its staging rows: released one task later,
                            // after the next task's first pass, instead of stalling the epilogue on the bulk-store read
@@ -447,21 +483,30 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       uint32_t va[32], vb[32];
       // ---- pass 1: row maximum; chunk c + 1 is being loaded from TMEM while chunk c is folded
       float mx = s_cls;
+      float mq[4] = {s_cls, s_cls, s_cls, s_cls};   // four independent chains: one chunk's 16 three-input maxima are not serial
       {
         auto fold = [&](const uint32_t(&v)[32], int c) {
-          if (c * 32 + 32 <= nvalid) {
+          if (kFull || c * 32 + 32 <= nvalid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
-              asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+              asm("max.f32 %0, %0, %1, %2;" : "+f"(mq[(j >> 1) & 3]) : "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
         };
+#ifdef HH_ATTN_X_NOMAX
+        mq[0] = 8.f;
+        if (false)
+#endif
         tmem_ld_32x32b_x32(s_col, va);
 #pragma unroll 1
+#ifdef HH_ATTN_X_NOMAX
+        for (int c = 0; c < 0; c += 2) {
+#else
         for (int c = 0; c < nch; c += 2) {
+#endif
           tmem_ld_wait();
           if (c + 1 < nch) tmem_ld_32x32b_x32(s_col + (c + 1) * 32, vb);
           fold(va, c);
@@ -471,6 +516,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             fold(vb, c + 1);
           }
         }
+        mx = fmaxf(fmaxf(mx, mq[0]), fmaxf(fmaxf(mq[1], mq[2]), mq[3]));
       }
       if (tr) trace_ev(p, 3 + jh, u, 1);
       if (release_st >= 0 && lane == 0) {
@@ -479,21 +525,37 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
       const float ml = mx * LOG2E;
       const float p_cls = fast_exp2(fmaf(s_cls, LOG2E, -ml));
+#ifndef HH_ATTN_NO_TURNS
+      // The exp pass is the one phase that saturates a shared unit (MUFU: 4 lanes per clock and scheduler).  The two warps
+      // of a scheduler (same TMEM lane quarter, one per half) take strict turns in it -- h0(u), h1(u), h0(u + 1), ... -- so
+      // one half's exponentials always run under the other half's MUFU-free phases (P V wait, read-out, next S, row
+      // maxima).  Left to themselves the two chains have the same period and nothing keeps them half a period apart:
+      // they drift into phase, share the MUFU during the exp pass and leave it idle for the rest of the period.
+      if (hf == 1) mbar_wait(&ex->x_done[0][wq], tp);
+      else if (u > 0) mbar_wait(&ex->x_done[1][wq], tp ^ 1u);
+#endif
+      if (tr) trace_ev(p, 3 + jh, u, 5);
 
       // ---- pass 2: P = exp2(S - max) as bf16 pairs (16 columns per 32 keys), the same double buffering.  P chunk c
       // overwrites S columns 16c .. 16c + 15, which belong to S chunk c / 2 <= c: already in registers.
-      float2 l2 = make_float2(0.f, 0.f);
+      float2 l2 = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
       {
         const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
         auto emit = [&](const uint32_t(&v)[32], int c) {
           uint32_t w[16];
-          if (c * 32 + 32 <= nvalid) {     // full chunk: no per-element masking code at all
+          if (kFull || c * 32 + 32 <= nvalid) {     // full chunk: no per-element masking code at all
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-              const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
-              l2 = __fadd2_rn(l2, e);
-              w[j >> 1] = pack_bf16x2(e.x, e.y);
+              if (((j >> 1) & 3) < HH_ATTN_EMU) {
+                const float2 e = poly_exp2x2(tt);
+                l2b = __fadd2_rn(l2b, e);
+                w[j >> 1] = pack_bf16x2(e.x, e.y);
+              } else {
+                const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
+                l2 = __fadd2_rn(l2, e);
+                w[j >> 1] = pack_bf16x2(e.x, e.y);
+              }
             }
           } else if (c < nch) {            // ragged last chunk (n = 196)
 #pragma unroll
@@ -522,7 +584,11 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           emit(vb, c + 1);
         }
       }
-      const float l = l2.x + l2.y + p_cls;
+      const float l = (l2.x + l2.y) + (l2b.x + l2b.y) + p_cls;
+#ifndef HH_ATTN_NO_TURNS
+      if (lane == 0) mbar_arrive(&ex->x_done[hf][wq]);
+#endif
+      if (tr) trace_ev(p, 3 + jh, u, 6);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -561,8 +627,10 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           st_shared_v4(sw128(stg, lane, half32 * 4 + c), w0, w1, w2, w3);
         }
       };
+#ifndef HH_ATTN_X_NOSTAGE
       stage(va, 0);
       stage(vb, 1);
+#endif
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -581,6 +649,12 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[TR_ROLES * TR_TASKS * TR_EVENTS + 2] = t;
+    p.trace[TR_ROLES * TR_TASKS * TR_EVENTS + 3] = static_cast<unsigned long long>(clock64());
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -641,7 +715,8 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    HH_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    HH_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    HH_CHECK_CUDA(cudaFuncSetAttribute(attn_space_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   TcArgs a;
@@ -655,21 +730,27 @@ int attn_space_tc(const bf16* qkv, bf16* out, int B, int T, int n, int H, float*
   static unsigned long long* trace_buf = nullptr;
   static const bool want_trace = std::getenv("HH_ATTN_TRACE") != nullptr;
   if (want_trace) {
-    if (!trace_buf) HH_CHECK_CUDA(cudaMalloc(&trace_buf, sizeof(unsigned long long) * TR_ROLES * TR_TASKS * TR_EVENTS));
-    HH_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * TR_ROLES * TR_TASKS * TR_EVENTS, stream));
+    if (!trace_buf) HH_CHECK_CUDA(cudaMalloc(&trace_buf, sizeof(unsigned long long) * (TR_ROLES * TR_TASKS * TR_EVENTS + 4)));
+    HH_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * (TR_ROLES * TR_TASKS * TR_EVENTS + 4), stream));
     a.trace = trace_buf;
   }
   const int ntasks = B * T * H;
   int grid = num_sms();
   if (grid > ntasks) grid = ntasks;
-  attn_space_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tm_in, tm_out, a);
+  if (n == ROWS) attn_space_tc_kernel<true><<<grid, NTHREADS, SMEM_BYTES, stream>>>(tm_in, tm_out, a);
+  else attn_space_tc_kernel<false><<<grid, NTHREADS, SMEM_BYTES, stream>>>(tm_in, tm_out, a);
   HH_CHECK_LAUNCH("attn_space_tc_kernel");
   if (want_trace) {  // debug only: dump the timeline of CTA 0 (ns relative to the first stamp)
-    static unsigned long long host[TR_ROLES * TR_TASKS * TR_EVENTS];
+    static unsigned long long host[TR_ROLES * TR_TASKS * TR_EVENTS + 4];
     HH_CHECK_CUDA(cudaStreamSynchronize(stream));
     HH_CHECK_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    {
+      const unsigned long long* ck = host + TR_ROLES * TR_TASKS * TR_EVENTS;
+      const double ns = static_cast<double>(ck[2] - ck[0]), cyc = static_cast<double>(ck[3] - ck[1]);
+      fprintf(stderr, "[attn trace] CTA 0 ran %.0f ns = %.0f SM cycles: %.3f GHz\n", ns, cyc, ns > 0 ? cyc / ns : 0.0);
+    }
     unsigned long long t0 = ~0ull;
-    for (unsigned long long v : host) if (v && v < t0) t0 = v;
+    for (int i = 0; i < TR_ROLES * TR_TASKS * TR_EVENTS; ++i) if (host[i] && host[i] < t0) t0 = host[i];
     const char* names[TR_ROLES] = {"producer", "mma", "helper", "softmax.h0", "softmax.h1", "-"};
     for (int r = 0; r < TR_ROLES - 1; ++r)
       for (int t = 0; t < TR_TASKS; ++t) {
