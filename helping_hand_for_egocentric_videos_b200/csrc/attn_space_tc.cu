@@ -19,7 +19,7 @@
 // Persistent CTA, 24 warps:
 //    0      TMA producer (4-D tensor maps, 128-row boxes: rows past n are zero-filled / clipped by hardware; the next
 //           task's tiles are in flight into the other smem stage while this one is processed)
-//    1      MMA issuer (one thread, polling);  2  TMEM allocator
+//    1, 3   MMA issuers (one thread per half, each blocking on its own chain of barriers);  2  TMEM allocator
 //    4-11   softmax + epilogue: ONE thread per query row (TMEM lane r = row r of a half, all 256 key columns), 4 warps per
 //           half.  512 threads leave 128 registers per thread: the next 32-column chunk's tcgen05.ld is in flight under
 //           the current chunk's arithmetic in both passes, and no cross-thread max / sum exchange (named barriers, shared
@@ -27,7 +27,10 @@
 //    12-15  legacy-MMA helpers (highest warp ids = highest issue priority, they gate the softmax warps): the CLS-key
 //           logit of every row (q_r . k_cls) and the CLS *query*'s partial softmax over this frame's keys (merged
 //           across frames by attn_cls_merge)
-// TMEM (512 columns), half h owns [256h, 256h+256): S; then P (bf16 pairs) in [0,128), O in [192,256).
+// TMEM (512 columns), half h owns [256h, 256h+256): S; then P (bf16 pairs) of keys 0..127 in [0,64), O in [64,128), P of
+// keys 128..255 in [128,192), the CLS key's probability (one K = 16 block) in [192,200).  P V runs in two parts: keys
+// 0..127 as soon as the first four chunks of the exp pass are written (under the second half of the pass), the rest
+// (+ the CLS value as a 17th K step against a [16 x 64] tile whose row 0 is v_cls) when the pass is done.
 #include <cstdio>
 #include <cstdlib>
 
@@ -44,6 +47,7 @@ constexpr int TILE_BYTES = ROWS * 128;    // 32 KB: [256 rows x 64 bf16], SWIZZL
 constexpr int STAGE_BYTES = 3 * TILE_BYTES;
 constexpr int NSTAGE = 2;
 constexpr int NCLS = 4;                     // CLS-vector ring: a slot is rewritten 4 tasks later, long after its readers
+constexpr int VCLS_BYTES = 16 * 128;        // [16 keys x 64] bf16 B tile of the CLS value: row 0 = v_cls, rows 1..15 zero
 constexpr int HALF_BYTES = TILE_BYTES / 2; // one 128-row box
 constexpr int NTHREADS = 512;                // 16 warps: 128 registers per thread
 constexpr float LOG2E = 1.4426950408889634f;
@@ -52,17 +56,16 @@ constexpr int PART = HD + 2;
 struct SmemExtras {
   __nv_bfloat16 cls_q[NCLS][HD];     // q, k, v of the CLS token for (clip, head): ring over the last NCLS tasks
   __nv_bfloat16 cls_k[NCLS][HD];
-  __nv_bfloat16 cls_v[NCLS][HD];
   float scls[NSTAGE][ROWS];          // CLS-key logit of every query row
   float merge[4][PART];              // CLS-query partials of the four helper warps
   uint64_t q_full[NSTAGE][2], k_full[NSTAGE], v_full[NSTAGE];      // per tile: Q rows of half h, K (+ CLS vectors), V
   uint64_t q_empty[NSTAGE][2], k_empty[NSTAGE], v_empty[NSTAGE];
   uint64_t scls_full[NSTAGE][2];     // CLS-key logits of half h's rows (helper warps 2h, 2h + 1)
-  uint64_t s_full[2], p_full[2], o_full[2], t_free[2];
+  uint64_t s_full[2], p_full[2][2], o_full[2], t_free[2];   // p_full[h][part]: P of keys 0..127 / 128..255 (+ CLS) written
   uint64_t x_done[2][4];             // exp pass of half h, TMEM lane quarter q finished (the turn passes to the other half)
   uint32_t tmem_slot;
 };
-constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + static_cast<int>(sizeof(SmemExtras)) + 64;
+constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + NCLS * VCLS_BYTES + static_cast<int>(sizeof(SmemExtras)) + 64;
 
 struct TcArgs {
   const bf16* qkv;
@@ -99,7 +102,7 @@ __device__ __forceinline__ uint32_t sw128(uint32_t tile, int row, int chunk) {
 // add), 2^f as a degree-3 polynomial (relative error 7.5e-5, well inside the bf16 rounding of P), n added into the
 // exponent field.  Clamped at -125: 2^-125 is nothing next to a row sum >= 1.
 #ifndef HH_ATTN_EMU
-#define HH_ATTN_EMU 1       // pairs out of every 4 that take this path in the exp pass (0 = all on the MUFU)
+#define HH_ATTN_EMU 0       // pairs out of every 4 that take this path in the exp pass (0 = all on the MUFU: measured best)
 #endif
 __device__ __forceinline__ float2 poly_exp2x2(float2 x) {
   const float MAGIC = 12582912.f;   // 1.5 * 2^23
@@ -124,7 +127,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                      const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemExtras* ex = reinterpret_cast<SmemExtras*>(smem + NSTAGE * STAGE_BYTES);
+  uint8_t* vcls = smem + NSTAGE * STAGE_BYTES;   // NCLS tiles of VCLS_BYTES (1024-byte aligned: two SWIZZLE_128B atoms each)
+  SmemExtras* ex = reinterpret_cast<SmemExtras*>(vcls + NCLS * VCLS_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = p.H * HD;
@@ -150,7 +154,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&ex->s_full[h], 1);
-      mbar_init(&ex->p_full[h], 4);
+      mbar_init(&ex->p_full[h][0], 4);
+      mbar_init(&ex->p_full[h][1], 4);
       mbar_init(&ex->o_full[h], 1);
       mbar_init(&ex->t_free[h], 4);
       for (int q = 0; q < 4; ++q) mbar_init(&ex->x_done[h][q], 1);
@@ -161,6 +166,8 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     tmem_alloc(&ex->tmem_slot, 512);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < NCLS * VCLS_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(vcls)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();   // rows 1..15 of the CLS-value tiles stay zero; row 0 is rewritten by the producer's bulk copies
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -191,7 +198,7 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const bf16* cls = p.qkv + static_cast<size_t>(b) * N * 3 * D + h * HD;
         bulk_load_1d(ex->cls_q[cs], cls, HD * 2, &ex->k_full[st]);
         bulk_load_1d(ex->cls_k[cs], cls + D, HD * 2, &ex->k_full[st]);
-        bulk_load_1d(ex->cls_v[cs], cls + 2 * D, HD * 2, &ex->k_full[st]);
+        bulk_load_1d(vcls + cs * VCLS_BYTES, cls + 2 * D, HD * 2, &ex->k_full[st]);   // row 0 of a swizzle atom is unswizzled
         mbar_wait(&ex->q_empty[st][0], ph ^ 1u);
         mbar_arrive_expect_tx(&ex->q_full[st][0], HALF_BYTES);
         tma_load_4d(&tm_in, &ex->q_full[st][0], base, h * HD, 0, f, b);
@@ -204,66 +211,57 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         tma_load_4d(&tm_in, &ex->q_full[st][1], base + HALF_BYTES, h * HD, 128, f, b);
       }
     }
-  } else if (warp == 1) {
-    // ================================================================== MMA issuer (one thread)
-    // The two halves are independent chains; each alternates between "S wanted" (its TMEM half is free, Q[h] and K
-    // have landed) and "P V wanted" (its P is in TMEM, V has landed).  The thread polls both with bounded try_waits and
-    // issues whatever is ready, so neither chain ever waits for the other's softmax.  Half 1 starts half a period late
-    // (after half 0's first P V), which puts the chains in anti-phase from the first task on.
+  } else if (warp == 1 || warp == 3) {
+    // ================================================================== MMA issuers: one thread per half
+    // Each half is an independent chain S -> P V (keys 0..127) -> P V (keys 128..255 + CLS) with its own issuing thread,
+    // which BLOCKS on the next barrier of its chain (wake-up ~90 cycles after the arrive).  One thread polling both
+    // chains with bounded mbarrier.try_wait reacted 3 000 - 7 000 cycles late: a try_wait on a barrier that does not
+    // complete suspends for a hardware time far above its hint (tools/ubench_mbar.cu).
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc_o = umma_idesc_bf16_bmn(128, HD);
-      int my_tasks = 0;
-      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) ++my_tasks;
-      int it[2] = {0, 0};
-      int stage_of[2] = {0, 0};       // 0: S wanted, 1: P V wanted
-      bool started1 = false;
-      while (it[0] < my_tasks || it[1] < my_tasks) {
+      const int hf = warp >> 1;
+      const uint32_t th = tmem_base + hf * 256;
+      int u = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++u) {
+        const int st = u & 1;
+        const uint32_t ph = (u >> 1) & 1;   // parity of the stage barriers
+        const uint32_t tp = u & 1;          // parity of the per-task barriers
+        const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
+        const uint32_t ks = qs + TILE_BYTES, vs = qs + 2 * TILE_BYTES;
+        mbar_wait(&ex->t_free[hf], tp ^ 1u);   // previous task's O has left these columns
+        mbar_wait(&ex->q_full[st][hf], ph);
+        mbar_wait(&ex->k_full[st], ph);
+        if (hf == 0) trace_ev(p, 1, u, 0);
+        tc_fence_after();
+        {
+          const uint64_t da = umma_desc_sw128(qs + hf * HALF_BYTES);
+          const uint64_t db = umma_desc_sw128(ks);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (it[hf] >= my_tasks) continue;
-          const int u = it[hf];
-          const int st = u & 1;
-          const uint32_t ph = (u >> 1) & 1;   // parity of the stage barriers
-          const uint32_t tp = u & 1;          // parity of the per-task barriers
-          const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
-          const uint32_t ks = qs + TILE_BYTES, vs = qs + 2 * TILE_BYTES;
-          if (stage_of[hf] == 0) {
-            if (hf == 1 && !started1) continue;
-            if (!mbar_try_wait_ns(&ex->t_free[hf], tp ^ 1u, 64)) continue;   // previous task's O has left these columns
-            if (!mbar_try_wait_ns(&ex->q_full[st][hf], ph, 64)) continue;
-            if (!mbar_try_wait_ns(&ex->k_full[st], ph, 64)) continue;
-            if (hf == 0) trace_ev(p, 1, u, 0);
-            tc_fence_after();
-            const uint64_t da = umma_desc_sw128(qs + hf * HALF_BYTES);
-            const uint64_t db = umma_desc_sw128(ks);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-              umma_bf16(tmem_base + hf * 256, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(&ex->s_full[hf]);
-            umma_commit(&ex->k_empty[st]);    // (with the other half's commit and the helpers) K may be refilled
-            trace_ev(p, 1, u, 1 + hf);
-            stage_of[hf] = 1;
-          } else {
-            if (!mbar_try_wait_ns(&ex->p_full[hf], tp, 64)) continue;
-            if (!mbar_try_wait_ns(&ex->v_full[st], ph, 64)) continue;
-            trace_ev(p, 1, u, 3 + 2 * hf);
-            tc_fence_after();
-            const uint64_t dv = umma_desc_sw128_mn(vs);
-#pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k) {  // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
-              const uint32_t pcol = 8 * k;   // P: 256 keys as 128 packed columns from column 0 of the half
-              umma_bf16_ts(tmem_base + hf * 256 + 192, tmem_base + hf * 256 + pcol, dv + static_cast<uint64_t>(k * 128),
-                           idesc_o, k > 0 ? 1u : 0u);
-            }
-            umma_commit(&ex->o_full[hf]);
-            umma_commit(&ex->v_empty[st]);
-            trace_ev(p, 1, u, 4 + 2 * hf);
-            stage_of[hf] = 0;
-            ++it[hf];
-            if (hf == 0) started1 = true;
-          }
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(th, da + 2 * k, db + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         }
+        umma_commit(&ex->s_full[hf]);
+        umma_commit(&ex->k_empty[st]);    // (with the other half's commit and the helpers) K may be refilled
+        trace_ev(p, 1, u, 1 + hf);
+        // P V, keys 0..127: P in columns [0, 64) of the half, O -> [64, 128) (S columns the exp pass has consumed)
+        mbar_wait(&ex->p_full[hf][0], tp);
+        mbar_wait(&ex->v_full[st], ph);
+        trace_ev(p, 1, u, 3 + 2 * hf);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_sw128_mn(vs);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // 16 keys per instruction = 2 swizzle atoms of V, 8 TMEM columns of P
+          umma_bf16_ts(th + 64, th + 8 * k, dv + static_cast<uint64_t>(k * 128), idesc_o, k > 0 ? 1u : 0u);
+        // keys 128..255: P in [128, 192); then the CLS key: probability block in [192, 200) against the v_cls tile
+        mbar_wait(&ex->p_full[hf][1], tp);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 8; k < 16; ++k)
+          umma_bf16_ts(th + 64, th + 64 + 8 * k, dv + static_cast<uint64_t>(k * 128), idesc_o, 1u);
+        umma_bf16_ts(th + 64, th + 192, umma_desc_sw128_mn(smem_u32(vcls + (u & (NCLS - 1)) * VCLS_BYTES)), idesc_o, 1u);
+        umma_commit(&ex->o_full[hf]);
+        umma_commit(&ex->v_empty[st]);
+        trace_ev(p, 1, u, 4 + 2 * hf);
       }
     }
   } else if (warp >= 12) {
@@ -458,8 +456,9 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     const int jh = hf;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(hf * 256);
     const uint32_t s_col = t_lane;            // this row's 256 S columns
-    const uint32_t p_col = t_lane;            // its 128 P columns (written behind the S columns already consumed)
-    const uint32_t o_col = t_lane + 192;      // its 64 O columns
+    const uint32_t o_col = t_lane + 64;       // its 64 O columns
+    // P chunk c (32 keys = 16 packed columns) goes behind the S columns already consumed: keys 0..127 -> [0, 64), keys
+    // 128..255 -> [128, 192) (chunk c <= 3: column 16c lies in S chunk c / 2; chunk c >= 4: 64 + 16c lies in S chunk c - 2 .. c)
     const int nvalid = kFull ? ROWS : min(ROWS, p.n);        // valid keys
     const int nch = kFull ? 8 : ((nvalid + 31) >> 5);        // 32-key chunks that hold valid keys (1..8)
     int u = 0;
@@ -471,8 +470,6 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       const uint32_t tp = u & 1;
       const int tk = HH_TASK(task); const int h = tk % p.H, f = (tk / p.H) % p.T, b = tk / (p.H * p.T);
       const uint32_t qs = smem_u32(smem + st * STAGE_BYTES);
-      const int cs = u & (NCLS - 1);
-      mbar_wait(&ex->k_full[st], ph);      // TMA-written cls_v visible to this thread
       mbar_wait(&ex->scls_full[st][hf], ph);
       const float s_cls = ex->scls[st][r];
       const bool tr = (wq == 0 && lane == 0);
@@ -536,52 +533,58 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 #endif
       if (tr) trace_ev(p, 3 + jh, u, 5);
 
-      // ---- pass 2: P = exp2(S - max) as bf16 pairs (16 columns per 32 keys), the same double buffering.  P chunk c
-      // overwrites S columns 16c .. 16c + 15, which belong to S chunk c / 2 <= c: already in registers.
+      // ---- pass 2: P = exp2(S - max) as bf16 pairs, 32 keys per iteration of ONE small loop body (next to the helper
+      // warps' code the hot loop stays in the instruction cache).  Software-pipelined by hand so that ptxas sees the
+      // tcgen05.ld and its consumer in the same block: the SCALED chunk t[] is carried across the back edge; an iteration
+      // first issues the load of the next chunk into x[] (dead), runs this chunk's exponentials on t[], and scales x[] into
+      // t[] at the bottom.  (A load whose consumer sits in the next iteration is sunk behind the last reader of its
+      // registers, i.e. to the end of the body, and its whole latency is exposed in every chunk.)
       float2 l2 = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
       {
         const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
-        auto emit = [&](const uint32_t(&v)[32], int c) {
+        uint32_t x[32];
+        float2 t[16];
+        tmem_ld_32x32b_x32(s_col, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          t[j] = __ffma2_rn(make_float2(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1])), sc, sh);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
           uint32_t w[16];
-          if (kFull || c * 32 + 32 <= nvalid) {     // full chunk: no per-element masking code at all
+          // unconditional (the last iteration re-reads chunk 0's columns, unused): a branch here would let the
+          // exponentials be hoisted above it and put the load back at the bottom of the body
+          tmem_ld_32x32b_x32(s_col + ((c + 1) & 7) * 32, x);
+          if (kFull || c < nch) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-              if (((j >> 1) & 3) < HH_ATTN_EMU) {
-                const float2 e = poly_exp2x2(tt);
-                l2b = __fadd2_rn(l2b, e);
-                w[j >> 1] = pack_bf16x2(e.x, e.y);
-              } else {
-                const float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
-                l2 = __fadd2_rn(l2, e);
-                w[j >> 1] = pack_bf16x2(e.x, e.y);
+            for (int j = 0; j < 16; ++j) {
+              float2 e;
+              if ((j & 3) < HH_ATTN_EMU) e = poly_exp2x2(t[j]);
+              else e = make_float2(fast_exp2(t[j].x), fast_exp2(t[j].y));
+              if (!kFull) {   // ragged last chunk (n = 196)
+                if (c * 32 + 2 * j >= nvalid) e.x = 0.f;
+                if (c * 32 + 2 * j + 1 >= nvalid) e.y = 0.f;
               }
-            }
-          } else if (c < nch) {            // ragged last chunk (n = 196)
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc, sh);
-              float2 e = make_float2(fast_exp2(tt.x), fast_exp2(tt.y));
-              if (c * 32 + j >= nvalid) e.x = 0.f;
-              if (c * 32 + j + 1 >= nvalid) e.y = 0.f;
-              l2 = __fadd2_rn(l2, e);
-              w[j >> 1] = pack_bf16x2(e.x, e.y);
+              if ((j & 3) < HH_ATTN_EMU) l2b = __fadd2_rn(l2b, e);
+              else l2 = __fadd2_rn(l2, e);
+              w[j] = pack_bf16x2(e.x, e.y);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = 0u;
           }
-          tmem_st_32x32b_x16(p_col + c * 16, w);
-        };
-        tmem_ld_32x32b_x32(s_col, va);
-#pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
-          if (c < nch) tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld_32x32b_x32(s_col + (c + 1) * 32, vb);
-          emit(va, c);
-          if (c + 1 < nch) tmem_ld_wait();
-          if (c + 2 < nch) tmem_ld_32x32b_x32(s_col + (c + 2) * 32, va);
-          emit(vb, c + 1);
+          // 16 packed columns behind the S columns already consumed: keys 0..127 -> [0, 64), keys 128..255 -> [128, 192)
+          tmem_st_32x32b_x16(t_lane + (c < 4 ? 16 * c : 64 + 16 * c), w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            t[j] = __ffma2_rn(make_float2(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1])), sc, sh);
+          if (c == 3) {   // keys 0..127 are written: their P V runs under the rest of the pass
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ex->p_full[hf][0]);
+          }
         }
       }
       const float l = (l2.x + l2.y) + (l2b.x + l2b.y) + p_cls;
@@ -589,10 +592,14 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       if (lane == 0) mbar_arrive(&ex->x_done[hf][wq]);
 #endif
       if (tr) trace_ev(p, 3 + jh, u, 6);
+      {   // the CLS key's probability as key 0 of a 17th K = 16 block (columns [192, 200)); its B tile holds v_cls in row 0
+        uint32_t wc[8] = {pack_bf16x2(p_cls, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st_32x32b_x8(t_lane + 192, wc);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ex->p_full[hf]);
+      if (lane == 0) mbar_arrive(&ex->p_full[hf][1]);
       if (tr) trace_ev(p, 3 + jh, u, 2);
 
       // ---- O = P V is in TMEM columns [192, 256) of this half: all 64 output dims of this row
@@ -606,25 +613,22 @@ attn_space_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&ex->t_free[hf]);   // the next task's S may overwrite this half
 
-      // ---- normalise (+ CLS value), stage the 64 bf16 values (128 B) of this row, bulk-store a 32-row x 128-B box
-      const float inv = 1.f / l;
-      const float pc = p_cls * inv;
+      // ---- normalise, stage the 64 bf16 values (128 B) of this row, bulk-store a 32-row x 128-B box
+      float inv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l));
+      const float2 inv2 = make_float2(inv, inv);
       // staging: the 4 KB of the (consumed) Q tile that belong to these 32 rows, SWIZZLE_128B
       const uint32_t stg = qs + static_cast<uint32_t>((jh * 128 + wq * 32) * 128);
       auto stage = [&](const uint32_t(&o)[32], int half32) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(&ex->cls_v[cs][half32 * 32 + c * 8]);
-          const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y), v2 = unpack_bf16x2(vv.z), v3 = unpack_bf16x2(vv.w);
-          const uint32_t w0 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 0]), inv, pc * v0.x),
-                                          fmaf(__uint_as_float(o[c * 8 + 1]), inv, pc * v0.y));
-          const uint32_t w1 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 2]), inv, pc * v1.x),
-                                          fmaf(__uint_as_float(o[c * 8 + 3]), inv, pc * v1.y));
-          const uint32_t w2 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 4]), inv, pc * v2.x),
-                                          fmaf(__uint_as_float(o[c * 8 + 5]), inv, pc * v2.y));
-          const uint32_t w3 = pack_bf16x2(fmaf(__uint_as_float(o[c * 8 + 6]), inv, pc * v3.x),
-                                          fmaf(__uint_as_float(o[c * 8 + 7]), inv, pc * v3.y));
-          st_shared_v4(sw128(stg, lane, half32 * 4 + c), w0, w1, w2, w3);
+          uint32_t wv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 r = __fmul2_rn(make_float2(__uint_as_float(o[c * 8 + 2 * q]), __uint_as_float(o[c * 8 + 2 * q + 1])), inv2);
+            wv[q] = pack_bf16x2(r.x, r.y);
+          }
+          st_shared_v4(sw128(stg, lane, half32 * 4 + c), wv[0], wv[1], wv[2], wv[3]);
         }
       };
 #ifndef HH_ATTN_X_NOSTAGE

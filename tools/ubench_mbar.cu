@@ -24,6 +24,22 @@ __device__ __forceinline__ void wait_mode(uint64_t* bar, uint32_t parity) {
       asm volatile("{ .reg .pred P; mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2; selp.b32 %0, 1, 0, P; }"
                    : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     }
+  } else if (MODE >= 4) {
+    // a thread that serves two barriers in turn: `bar + 1` never completes, `bar` is the one that is signalled
+    const uint32_t ns = MODE == 4 ? 64u : (MODE == 5 ? 0u : 16u);
+    for (;;) {
+      if (MODE == 7) {
+        uint32_t ok = 0;
+        asm volatile("{ .reg .pred P; mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2; selp.b32 %0, 1, 0, P; }"
+                     : "=r"(ok) : "r"(smem_u32(bar + 1)), "r"(0u) : "memory");
+        asm volatile("{ .reg .pred P; mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2; selp.b32 %0, 1, 0, P; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+      } else {
+        if (mbar_try_wait_ns(bar + 1, 0, ns)) break;
+        if (mbar_try_wait_ns(bar, parity, ns)) break;
+      }
+    }
   } else {
     uint32_t ok = 0;
     while (!ok) {
@@ -36,11 +52,13 @@ __device__ __forceinline__ void wait_mode(uint64_t* bar, uint32_t parity) {
 // NW waiting warps (1 = only warp 0; 5 = warps 0, 4..7 also wait: several sleepers on the barrier's CTA)
 template <int MODE>
 __global__ void k(long long* out, int delay) {
-  __shared__ uint64_t bar, back;
+  __shared__ uint64_t bars[2], back;
+  uint64_t& bar = bars[0];
   __shared__ long long t_arrive[ROUNDS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     mbar_init(&back, 1);
     fence_mbar_init();
   }
@@ -87,6 +105,10 @@ int main() {
     run<1>("try_wait, 64 ns hint", delay);
     run<2>("try_wait, no hint", delay);
     run<3>("test_wait spin", delay);
+    run<4>("two barriers in turn, try_wait 64 ns", delay);
+    run<6>("two barriers in turn, try_wait 16 ns", delay);
+    run<5>("two barriers in turn, try_wait 0 ns", delay);
+    run<7>("two barriers in turn, test_wait", delay);
   }
   return 0;
 }
