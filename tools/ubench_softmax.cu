@@ -156,6 +156,56 @@ __device__ __forceinline__ float exp_pass(uint32_t s_col, float ml) {
   return l2.x + l2.y;
 }
 
+// three-stage register pipeline (x <- ld(c+1), t = scaled c, e = 2^t of c-1), G = columns per iteration (32 or 16)
+template <int G>
+__device__ __forceinline__ float exp_pass_pipe(uint32_t s_col, float ml) {
+  constexpr int NP = G / 2, NI = 256 / G;
+  const float2 sc = make_float2(LOG2E, LOG2E), sh = make_float2(-ml, -ml);
+  uint32_t x[G];
+  float2 t[NP], e[NP];
+  float2 l2 = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
+  auto ld = [&](int c) {
+    if constexpr (G == 32) tmem_ld_32x32b_x32(s_col + c * G, reinterpret_cast<uint32_t(&)[32]>(x));
+    else tmem_ld_32x32b_x16(s_col + c * G, reinterpret_cast<uint32_t(&)[16]>(x));
+  };
+  auto scale = [&]() {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) t[j] = ffma2(make_float2(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1])), sc, sh);
+  };
+  auto exps = [&]() {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) e[j] = make_float2(fast_exp2(t[j].x), fast_exp2(t[j].y));
+  };
+  auto emitp = [&](int c) {
+    uint32_t w[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (j & 1) l2b = fadd2(l2b, e[j]); else l2 = fadd2(l2, e[j]);
+      w[j] = pack_bf16x2(e[j].x, e[j].y);
+    }
+    if constexpr (G == 32) tmem_st_32x32b_x16(s_col + c * NP, reinterpret_cast<uint32_t(&)[16]>(w));
+    else tmem_st_32x32b_x8(s_col + c * NP, reinterpret_cast<uint32_t(&)[8]>(w));
+  };
+  ld(0);
+  tmem_ld_wait();
+  scale();
+  ld(1);
+  exps();
+  tmem_ld_wait();
+  scale();
+#pragma unroll 1
+  for (int c = 1; c < NI; ++c) {
+    ld((c + 1) & (NI - 1));
+    emitp(c - 1);
+    exps();
+    tmem_ld_wait();
+    scale();
+  }
+  emitp(NI - 1);
+  tmem_st_wait();
+  return l2.x + l2.y + l2b.x + l2b.y;
+}
+
 // ---------------------------------------------------------------- max-pass variants
 template <int MODE>
 __device__ __forceinline__ float max_pass(uint32_t s_col) {
@@ -201,7 +251,7 @@ __device__ __forceinline__ float max_pass(uint32_t s_col) {
 // test ids: 0..7 exp pass MODE, 10..12 max pass MODE, 20: max pass (4 chains) + exp pass MODE 1 back to back
 // BG: tensor-core work running next to the softmax warps (warp 8, one thread): 0 none, 1 S-like (128x256x64 from shared
 // memory into TMEM columns [256, 512)), 2 P V-like (A = 128 TMEM columns, B from shared memory, N = 64), 3 both in turn
-template <int TEST, int BG>
+template <int TEST, int BG, int COMP = 0>
 __global__ void __launch_bounds__(512, 1) bench_kernel(long long* out, float* sink) {
   __shared__ uint32_t tmem_slot;
   __shared__ uint64_t bg_bar;
@@ -225,7 +275,7 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(long long* out, float* si
   const uint32_t s_col = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(hf * 256);
   float acc = 0.f;
   long long t0 = 0, t1 = 0;
-  const int nsoft = BG ? 4 : min(8, static_cast<int>(blockDim.x) / 32);
+  const int nsoft = (BG || COMP) ? 4 : min(8, static_cast<int>(blockDim.x) / 32);
   if (warp < nsoft) {
     // fill the 256 columns with logits around 0 (|s| < 8)
     uint32_t w[16];
@@ -242,7 +292,9 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(long long* out, float* si
     t0 = clock64();
 #pragma unroll 1
     for (int r = 0; r < REPS; ++r) {
-      if (TEST < 10) acc += exp_pass<TEST>(s_col, 8.f * LOG2E + acc * 1e-30f);
+      if (TEST == 8) acc += exp_pass_pipe<32>(s_col, 8.f * LOG2E + acc * 1e-30f);
+      else if (TEST == 9) acc += exp_pass_pipe<16>(s_col, 8.f * LOG2E + acc * 1e-30f);
+      else if (TEST < 10) acc += exp_pass<TEST>(s_col, 8.f * LOG2E + acc * 1e-30f);
       else if (TEST < 20) acc += max_pass<TEST - 10>(s_col);
       else {
         const float mx = max_pass<1>(s_col);
@@ -250,6 +302,21 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(long long* out, float* si
       }
     }
     t1 = clock64();
+  }
+  if (COMP != 0 && warp >= 4 && warp < 8) {   // a different instruction stream on the same schedulers
+    const uint32_t c_col = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + 256u;
+    float a = static_cast<float>(threadIdx.x), b = 1.0001f, cacc = 0.f;
+    while (!stop_flag) {
+      if (COMP == 1) cacc += max_pass<1>(c_col);
+      else if (COMP == 2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) { a = fmaf(a, b, 0.5f); b = fmaf(b, 1.0001f, a * 1e-9f); }
+        cacc += a + b;
+      } else {
+        __nanosleep(200);
+      }
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = cacc;
   }
   if (BG != 0 && warp == 8 && lane == 0) {
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
@@ -292,16 +359,16 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(long long* out, float* si
   }
 }
 
-template <int TEST, int BG = 0>
+template <int TEST, int BG = 0, int COMP = 0>
 void run(const char* name, int threads) {
   long long* d_out;
   float* d_sink;
   const int grid = 148;
   cudaMalloc(&d_out, sizeof(long long) * grid * 17);
-  if (BG) cudaFuncSetAttribute(bench_kernel<TEST, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+  if (BG) cudaFuncSetAttribute(bench_kernel<TEST, BG, COMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
   cudaMalloc(&d_sink, sizeof(float) * grid * 512);
   cudaMemset(d_out, 0, sizeof(long long) * grid * 16);
-  for (int i = 0; i < 3; ++i) bench_kernel<TEST, BG><<<grid, BG ? 288 : threads, BG ? 66 * 1024 : 0>>>(d_out, d_sink);
+  for (int i = 0; i < 3; ++i) bench_kernel<TEST, BG, COMP><<<grid, (BG || COMP) ? 288 : threads, BG ? 66 * 1024 : 0>>>(d_out, d_sink);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("%s: CUDA error %s\n", name, cudaGetErrorString(e));
@@ -330,6 +397,16 @@ void run(const char* name, int threads) {
 
 int main() {
   // softmax warps of half 0 only (128 threads) with the tensor core busy on half 1
+  run<8, 0, 1>("exp 3-stage x32 | max-pass loop on the other warp", 128);
+  run<8, 0, 2>("exp 3-stage x32 | FFMA loop on the other warp", 128);
+  run<8, 0, 3>("exp 3-stage x32 | sleeping other warp", 128);
+  run<0, 0, 1>("exp shipped | max-pass loop on the other warp", 128);
+  run<0, 0, 2>("exp shipped | FFMA loop on the other warp", 128);
+  run<8, 3, 1>("exp 3-stage x32 | max-pass loop + MMAs", 128);
+  run<8, 0>("exp 3-stage x32, no MMA", 128);
+  run<8, 3>("exp 3-stage x32 + both MMA kinds", 128);
+  run<9, 0>("exp 3-stage x16, no MMA", 128);
+  run<9, 3>("exp 3-stage x16 + both MMA kinds", 128);
   run<0, 0>("exp shipped, no MMA (288-thread CTA)", 128);
   run<0, 1>("exp shipped + S-like MMAs", 128);
   run<0, 2>("exp shipped + P V-like MMAs", 128);
@@ -349,6 +426,8 @@ int main() {
     run<5>("exp: 100% on the FMA pipe", threads);
     run<6>("exp: ex2 batched 8 ahead", threads);
     run<7>("exp: no ex2 (scale + sum + pack)", threads);
+    run<8>("exp: 3-stage register pipeline, x32", threads);
+    run<9>("exp: 3-stage register pipeline, x16", threads);
     run<10>("max: 1 chain", threads);
     run<11>("max: 4 chains", threads);
     run<12>("max: loads only", threads);
