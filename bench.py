@@ -286,8 +286,12 @@ class TrainShare:
         return (self.clip.visual.flops_per_clip() + self.model.flops_per_clip(self.T)
                 + self.R * self.clip.text_flops_per_sequence())
 
-    def step(self, video=None, timed_parts=False):
+    def step(self, video=None, timed_parts=False, wrap=None):
+        """`wrap`: optional {"decoder" | "backward": context-manager factory} put around that part (tools/prof_c4.py)."""
+        import contextlib
         from helping_hand_for_egocentric_videos_b200 import parallel
+        wrap = wrap or {}
+        around = lambda k: wrap[k]() if k in wrap else contextlib.nullcontext()  # noqa: E731
         from helping_hand_for_egocentric_videos_b200.model import box_utils, loss, metric
         B, T, R = self.B, self.T, self.R
         video = self.video if video is None else video
@@ -299,7 +303,8 @@ class TrainShare:
         if ev:
             ev[1].record()
         grid = out["image_feature_map"][:, 1:].unflatten(1, (T, 256))
-        mo, hs, _, _ = self.model(grid)
+        with around("decoder"):
+            mo, hs, _, _ = self.model(grid)
         if ev:
             ev[2].record()
         txt = self.model.txt_proj(out["text_feature_map"][self.ar, self.tokens.argmax(-1)])
@@ -317,7 +322,8 @@ class TrainShare:
         total = nce + lh + lo_ + 0.5 * word
         if ev:
             ev[3].record()
-        total.backward()
+        with around("backward"):
+            total.backward()
         if ev:
             ev[4].record()
         self.opt.step()
