@@ -366,7 +366,7 @@ expand_rows_scalar_kernel(const float* __restrict__ src, float* __restrict__ dst
 
 }  // namespace
 
-int linear_f32(const LinArgs& a, cudaStream_t stream) {
+int linear_f32_legacy(const LinArgs& a, cudaStream_t stream) {
   HH_REQUIRE(a.R > 0 && a.N > 0 && a.K > 0, "linear_f32: empty problem");
   HH_REQUIRE(a.K % LBK == 0 && a.ldi % 4 == 0, "linear_f32: K must be a multiple of 32 and ldi of 4");
   HH_REQUIRE(a.in_add == nullptr || a.add_mod > 0, "linear_f32: add_mod");

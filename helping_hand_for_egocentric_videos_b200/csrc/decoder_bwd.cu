@@ -543,7 +543,7 @@ transpose_bf16_kernel(const T* __restrict__ in, long long ld, bf16* __restrict__
 }  // namespace
 
 // ================================================================================================ host wrappers
-int linear_dgrad_f32(const LinBwdArgs& a_in, cudaStream_t s) {
+int linear_dgrad_f32_legacy(const LinBwdArgs& a_in, cudaStream_t s) {
   LinBwdArgs a = a_in;
   HH_REQUIRE(a.R > 0 && a.N > 0 && a.K > 0 && a.dY && a.W && a.dX, "linear_dgrad: bad argument");
   HH_REQUIRE(a.act == 0 || a.Y != nullptr, "linear_dgrad: activation derivative needs the saved output");
@@ -565,7 +565,7 @@ int linear_dgrad_f32(const LinBwdArgs& a_in, cudaStream_t s) {
   return 0;
 }
 
-int linear_wgrad_f32(const LinBwdArgs& a_in, cudaStream_t s) {
+int linear_wgrad_f32_legacy(const LinBwdArgs& a_in, cudaStream_t s) {
   LinBwdArgs a = a_in;
   HH_REQUIRE(a.R > 0 && a.N > 0 && a.K > 0 && a.dY && a.X && a.dW, "linear_wgrad: bad argument");
   HH_REQUIRE(a.act == 0 || a.Y != nullptr, "linear_wgrad: activation derivative needs the saved output");

@@ -136,7 +136,8 @@ struct LinArgs {
   int in_relu;                            // 1: apply ReLU to the input first (txt_proj = ReLU -> Linear)
   DropCfg drop; uint32_t drop_site;       // training: dropout on act(x W^T + b) before the residual add, idx = row*N + col
 };
-int linear_f32(const LinArgs& a, cudaStream_t stream);
+int linear_f32(const LinArgs& a, cudaStream_t stream);          // lin3.cu (pipelined); shapes it refuses go to:
+int linear_f32_legacy(const LinArgs& a, cudaStream_t stream);   // decoder.cu (also with HH_LIN_LEGACY=1)
 // Query self-attention: q,k,v fp32 [B*Q, C] (q pre-scaled), heads of 64 -> out fp32 [B*Q, C].
 // drop: dropout on the attention probabilities (training), idx = ((b*heads + h)*Q + i)*Q + j
 int self_attn_queries(const float* q, const float* k, const float* v, int ld, float* out, int B, int Q, int heads,
@@ -192,6 +193,8 @@ struct LinBwdArgs {
 };
 int linear_dgrad_f32(const LinBwdArgs& a, cudaStream_t s);
 int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s);
+int linear_dgrad_f32_legacy(const LinBwdArgs& a, cudaStream_t s);
+int linear_wgrad_f32_legacy(const LinBwdArgs& a, cudaStream_t s);
 // LayerNorm backward over rows of x (+ optional bf16 delta, as in the forward).  dy fp32 or bf16 (row stride lddy).
 // dx = beta_dx * dx + grad (fp32, contiguous rows) and/or dx16 (bf16);  dgamma/dbeta = beta_w * old + sum over rows.
 struct LnBwdArgs {
