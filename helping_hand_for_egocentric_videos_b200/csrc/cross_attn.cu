@@ -185,7 +185,8 @@ cross_attn_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, c
 }
 
 __global__ void __launch_bounds__(HD)
-cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int Q, int heads, int nparts, float oscale) {
+cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, float* __restrict__ lse, int Q, int heads,
+                   int nparts, float oscale) {
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
   const int d = threadIdx.x;
   const int C = heads * HD;
@@ -201,6 +202,8 @@ cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, int 
       oo += pr[2 + d] * c;
     }
     out[static_cast<size_t>(b * Q + i) * C + h * HD + d] = oo * oscale / ll;
+    // log-sum-exp of the row's logits, kept for cross_attn_bwd (dropout does not enter: it acts after normalisation)
+    if (lse != nullptr && d == 0) lse[static_cast<size_t>(blockIdx.x) * Q + i] = mm + logf(ll);
   }
 }
 
@@ -220,7 +223,7 @@ size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S) {
 }
 
 int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
-               void* workspace, cudaStream_t stream, DropCfg drop, uint32_t drop_site) {
+               void* workspace, cudaStream_t stream, DropCfg drop, uint32_t drop_site, float* lse_out) {
   HH_REQUIRE(drop.thr == 0 || S % 8 == 0, "cross_attn: dropout needs a multiple of 8 keys");
   HH_REQUIRE(Q >= 1 && Q <= XQ, "cross_attn: 1..16 queries supported");
   HH_REQUIRE(ldkv % 8 == 0, "cross_attn: K/V row stride must be a multiple of 8 elements");
@@ -241,7 +244,7 @@ int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* ou
   cross_attn_mma_kernel<<<B * heads * splits, XW * 32, smem, stream>>>(q, K, V, ldkv, static_cast<float*>(workspace), Q,
                                                                       heads, S, splits, keys_per_warp, drop, drop_site);
   HH_CHECK_LAUNCH("cross_attn_mma_kernel");
-  cross_merge_kernel<<<B * heads, HD, 0, stream>>>(static_cast<const float*>(workspace), out, Q, heads, nparts,
+  cross_merge_kernel<<<B * heads, HD, 0, stream>>>(static_cast<const float*>(workspace), out, lse_out, Q, heads, nparts,
                                                    drop.thr ? drop.scale : 1.f);
   HH_CHECK_LAUNCH("cross_merge_kernel");
   return 0;

@@ -357,10 +357,11 @@ self_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, c
 }
 
 // ------------------------------------------------------------------------------------------ cross-attention backward
-// (i) per (clip, head): lse_i over the S keys and D_i = dO_i . O_i.  Warp i owns query row i; lanes stride over keys.
+// (i) per (clip, head): lse_i over the S keys -- only when the forward did not keep it (cross_attn's lse_out).  Warp i owns
+// query row i; lanes stride over keys.
 __global__ void __launch_bounds__(512)
-cross_stats_kernel(const float* __restrict__ q, const bf16* __restrict__ K, int ldkv, const float* __restrict__ dO,
-                   const float* __restrict__ O, float* __restrict__ lse, float* __restrict__ Dv, int Q, int heads, int S) {
+cross_stats_kernel(const float* __restrict__ q, const bf16* __restrict__ K, int ldkv, float* __restrict__ lse, int Q,
+                   int heads, int S) {
   __shared__ float qs[16][HD];
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
   const int C = heads * HD;
@@ -388,20 +389,14 @@ cross_stats_kernel(const float* __restrict__ q, const bf16* __restrict__ K, int 
     sacc = (m == -INFINITY ? 0.f : sacc * __expf(m - nm)) + (om == -INFINITY ? 0.f : os * __expf(om - nm));
     m = nm;
   }
-  const float* g = dO + static_cast<size_t>(b * Q + i) * C + h * HD;
-  const float* o = O + static_cast<size_t>(b * Q + i) * C + h * HD;
-  float t = g[lane] * o[lane] + g[lane + 32] * o[lane + 32];
-  t = warp_sum(t);
-  if (lane == 0) {
-    lse[(static_cast<size_t>(b) * heads + h) * Q + i] = m + logf(sacc);
-    Dv[(static_cast<size_t>(b) * heads + h) * Q + i] = t;
-  }
+  if (lane == 0) lse[(static_cast<size_t>(b) * heads + h) * Q + i] = m + logf(sacc);
 }
 
-// (ii) one thread per key: p_ij, dS_ij, dV_j = sum_i p_ij dO_i, dK_j = sum_i dS_ij q_i
+// (ii) one thread per key: p_ij, dS_ij, dV_j = sum_i p_ij dO_i, dK_j = sum_i dS_ij q_i;  D_i = dO_i . O_i is recomputed by
+// every CTA of the (clip, head) (13 x 64 products) instead of a pass of its own
 __global__ void __launch_bounds__(128)
 cross_keys_kernel(const float* __restrict__ q, const bf16* __restrict__ K, const bf16* __restrict__ V, int ldkv,
-                  const float* __restrict__ dO, const float* __restrict__ lse, const float* __restrict__ Dv,
+                  const float* __restrict__ dO, const float* __restrict__ O, const float* __restrict__ lse,
                   bf16* __restrict__ dK, bf16* __restrict__ dV, int lddkv, float* __restrict__ dS, int Q, int heads, int S,
                   DropCfg drop, uint32_t drop_site) {
   __shared__ float qs[16][HD], gs[16][HD];
@@ -412,9 +407,13 @@ cross_keys_kernel(const float* __restrict__ q, const bf16* __restrict__ K, const
     qs[i / HD][i % HD] = q[static_cast<size_t>(b * Q + i / HD) * C + h * HD + i % HD];
     gs[i / HD][i % HD] = dO[static_cast<size_t>(b * Q + i / HD) * C + h * HD + i % HD];
   }
-  if (threadIdx.x < Q) {
-    ls[threadIdx.x] = lse[(static_cast<size_t>(b) * heads + h) * Q + threadIdx.x];
-    ds_[threadIdx.x] = Dv[(static_cast<size_t>(b) * heads + h) * Q + threadIdx.x];
+  if (threadIdx.x < Q) ls[threadIdx.x] = lse[(static_cast<size_t>(b) * heads + h) * Q + threadIdx.x];
+  for (int i = threadIdx.x >> 5; i < Q; i += 4) {
+    const int lane = threadIdx.x & 31;
+    const float* g = dO + static_cast<size_t>(b * Q + i) * C + h * HD;
+    const float* o = O + static_cast<size_t>(b * Q + i) * C + h * HD;
+    const float t = warp_sum(g[lane] * o[lane] + g[lane + 32] * o[lane + 32]);
+    if (lane == 0) ds_[i] = t;
   }
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,21 +630,24 @@ int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const 
 }
 
 size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S) {
-  return static_cast<size_t>(B) * heads * Q * (static_cast<size_t>(S) + 2) * sizeof(float);
+  return static_cast<size_t>(B) * heads * Q * (static_cast<size_t>(S) + 1) * sizeof(float);
 }
 
 int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
                    bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
-                   DropCfg drop, uint32_t drop_site) {
+                   DropCfg drop, uint32_t drop_site, const float* lse_saved) {
   HH_REQUIRE(B > 0 && Q >= 1 && Q <= 16 && heads > 0 && S > 0, "cross_attn_bwd: 1..16 queries");
   HH_REQUIRE(q && K && V && O && dO && dq && dK && dV && workspace, "cross_attn_bwd: null buffer");
   HH_REQUIRE(ldkv % 8 == 0 && lddkv % 2 == 0, "cross_attn_bwd: row pitch");
-  float* lse = static_cast<float*>(workspace);
-  float* Dv = lse + static_cast<size_t>(B) * heads * Q;
-  float* dS = Dv + static_cast<size_t>(B) * heads * Q;
-  cross_stats_kernel<<<B * heads, 32 * Q, 0, s>>>(q, K, ldkv, dO, O, lse, Dv, Q, heads, S);
+  float* lse_ws = static_cast<float*>(workspace);
+  float* dS = lse_ws + static_cast<size_t>(B) * heads * Q;
+  const float* lse = lse_saved;
+  if (lse == nullptr) {
+    cross_stats_kernel<<<B * heads, 32 * Q, 0, s>>>(q, K, ldkv, lse_ws, Q, heads, S);
+    lse = lse_ws;
+  }
   dim3 grid((S + 127) / 128, B * heads);
-  cross_keys_kernel<<<grid, 128, 0, s>>>(q, K, V, ldkv, dO, lse, Dv, dK, dV, lddkv, dS, Q, heads, S, drop, drop_site);
+  cross_keys_kernel<<<grid, 128, 0, s>>>(q, K, V, ldkv, dO, O, lse, dK, dV, lddkv, dS, Q, heads, S, drop, drop_site);
   cross_dq_kernel<<<B * heads, 256, 0, s>>>(dS, K, ldkv, dq, Q, heads, S);
   HH_CHECK_LAUNCH("cross_attn_bwd kernels");
   return 0;

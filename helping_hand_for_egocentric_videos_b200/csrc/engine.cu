@@ -594,11 +594,12 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
       float* o = t2 + RC_;
       float* qkv = o + RC_;
       float* ffn = qkv + 3 * RC_;
-      for (auto& b : saved) b = LayerBufs{tgt, tgt, tgt, tgt, t2, t2, t2, qkv, o, qkv, o, ffn};
+      for (auto& b : saved) b = LayerBufs{tgt, tgt, tgt, tgt, t2, t2, t2, qkv, o, qkv, o, ffn, nullptr};
       saved_B = 0;
     } else {
       const size_t per = 12 * RC_ + static_cast<size_t>(R) * Fd;  // x0,x1,x2,n1,n2,n3 (6) qkv (3) o1,qc,o2 (3) + f
-      RC(ws_train.reserve((per * Lr + RC_) * 4));
+      const size_t nlse = static_cast<size_t>(B) * heads * Q;     // cross-attention lse per layer (after the last x3)
+      RC(ws_train.reserve((per * Lr + RC_ + nlse * Lr) * 4));
       float* p0 = static_cast<float*>(ws_train.ptr);
       for (int i = 0; i < Lr; ++i) {
         float* b = p0 + per * i;
@@ -606,6 +607,7 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
         L.x0 = b; L.x1 = b + RC_; L.x2 = b + 2 * RC_; L.n1 = b + 3 * RC_; L.n2 = b + 4 * RC_; L.n3 = b + 5 * RC_;
         L.qkv = b + 6 * RC_; L.o1 = b + 9 * RC_; L.qc = b + 10 * RC_; L.o2 = b + 11 * RC_; L.f = b + 12 * RC_;
         L.x3 = (i + 1 < Lr) ? p0 + per * (i + 1) : p0 + per * Lr;  // = x0 of the next layer
+        L.lse = p0 + per * Lr + RC_ + nlse * i;
       }
       tgt = saved[0].x0;
       saved_B = B;
@@ -659,7 +661,7 @@ int Decoder::forward(const float* features, int64_t stride_b, int64_t stride_row
     PROF(K_DEC_QUERY, lin(A.n2, C, qpos, Q, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C,
            static_cast<const float*>(b_caq.ptr) + static_cast<size_t>(i) * C, nullptr, 0, A.qc, C, R, C, C, 0, s));
     PROF(K_DEC_CROSS, cross_attn(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, B, Q, heads, S,
-                  ws_cross.ptr, s, dr, i * 8 + 2));
+                  ws_cross.ptr, s, dr, i * 8 + 2, A.lse));
     PROF(K_DEC_QUERY, lin(A.o2, C, nullptr, 0, weights.get(p + "multihead_attn.out_proj.weight"), weights.get(p + "multihead_attn.out_proj.bias"),
            A.x1, C, A.x2, C, R, C, C, 0, s, dr, i * 8 + 3));
     // FFN (:457-459)

@@ -101,6 +101,7 @@ struct Decoder {
     float *qkv, *o1;            // self-attention packed projections (q pre-scaled) and core output
     float *qc, *o2;             // cross-attention query projection (pre-scaled) and core output
     float* f;                   // FFN hidden after ReLU
+    float* lse;                 // training only: cross-attention row log-sum-exp [B*heads, Q] (nullptr in inference)
   };
   std::vector<LayerBufs> saved;
   int saved_B = 0, saved_T = 0;

@@ -26,17 +26,19 @@ namespace hh {
 namespace {
 
 // dhsproj[lb, q, :] = sum_t dcond[lb, t, q, :] ;  dft[t, :] = sum_{lb, q} dcond[lb, t, q, :]
+// (blockIdx.y + y_off selects the row: [0, LB*Q) the dhsproj rows, then the T rows of dft)
 __global__ void frame_term_bwd_kernel(const float* __restrict__ dcond, float* __restrict__ dhsproj, float* __restrict__ dft,
-                                      int LB, int T, int Q, int C) {
+                                      int LB, int T, int Q, int C, int y_off) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (blockIdx.y < static_cast<unsigned>(LB * Q)) {
-    const int lb = blockIdx.y / Q, q = blockIdx.y % Q;
+  const int by = static_cast<int>(blockIdx.y) + y_off;
+  if (by < LB * Q) {
+    const int lb = by / Q, q = by % Q;
     float t = 0.f;
     for (int f = 0; f < T; ++f) t += dcond[((static_cast<size_t>(lb) * T + f) * Q + q) * C + c];
     dhsproj[(static_cast<size_t>(lb) * Q + q) * C + c] = t;
   } else {
-    const int f = blockIdx.y - LB * Q;
+    const int f = by - LB * Q;
     float t = 0.f;
     for (int lb = 0; lb < LB; ++lb)
       for (int q = 0; q < Q; ++q) t += dcond[((static_cast<size_t>(lb) * T + f) * Q + q) * C + c];
@@ -136,6 +138,8 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
   if (w3 > wsb) wsb = w3;
   const size_t w4 = colsum_workspace_bytes(static_cast<long long>(LC));
   if (w4 > wsb) wsb = w4;
+  const size_t w5 = colsum_workspace_bytes(static_cast<long long>(T) * Q * C);   // frame-term reduction
+  if (w5 > wsb) wsb = w5;
   RC(bw_ws.reserve(wsb));
   float* ga = static_cast<float*>(bw_a.ptr);
   float* gb = static_cast<float*>(bw_b.ptr);
@@ -175,8 +179,20 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
       // cond[lb,t,q] = hs[lb,q] Wf1^T + (frame_index[t] Wf2^T + bf)      (tfm_decoder.py:212-215)
       float* dhsproj = gb;
       float* dft = gb + LR * C;
-      dim3 grid((C + 127) / 128, static_cast<unsigned>(LR + T));
-      frame_term_bwd_kernel<<<grid, 128, 0, s>>>(ga, dhsproj, dft, Lr * B, T, Q, C);
+      float* dsum = dft + static_cast<size_t>(T) * C;   // [T, Q, C]: d cond summed over (layer, clip)
+      if (static_cast<size_t>(T) * Q * C + LR * C + static_cast<size_t>(T) * C <= big) {
+        // dft sums 4992 rows per output at the c4 shape: the (layer, clip) reduction goes through the 64-way column-sum
+        // kernels first (one thread per output walking all rows took 0.83 ms), the T rows of dft only sum Q rows then
+        dim3 grid((C + 127) / 128, static_cast<unsigned>(LR));
+        frame_term_bwd_kernel<<<grid, 128, 0, s>>>(ga, dhsproj, dft, Lr * B, T, Q, C, 0);
+        const long long tqc = static_cast<long long>(T) * Q * C;
+        RC(colsum_rows(ga, 0, tqc, static_cast<long long>(Lr) * B, tqc, 0.f, dsum, bw_ws.ptr, s));
+        dim3 grid2((C + 127) / 128, static_cast<unsigned>(T));
+        frame_term_bwd_kernel<<<grid2, 128, 0, s>>>(dsum, dhsproj, dft, 1, T, Q, C, Q);
+      } else {
+        dim3 grid((C + 127) / 128, static_cast<unsigned>(LR + T));
+        frame_term_bwd_kernel<<<grid, 128, 0, s>>>(ga, dhsproj, dft, Lr * B, T, Q, C, 0);
+      }
       HH_CHECK_LAUNCH("frame_term_bwd_kernel");
       float* dWf = G("frame_proj.weight");  // [C, 2C] = [Wf1 | Wf2]
       RC(wgrad(dhsproj, C, nullptr, 0, 0, hs, C, nullptr, 0, dWf, 2 * C, nullptr, static_cast<int>(LR), C, C, 0.f, 1.f, s));
@@ -221,7 +237,7 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "multihead_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s, dr, st0 + 3));  // tmp = d o2
     RC(cross_attn_bwd(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, tmp, tmp2,
                       dKall + static_cast<size_t>(i) * C, dVall + static_cast<size_t>(i) * C, Lr * C, B, Q, heads, S, bw_ws.ptr, s,
-                      dr, st0 + 2));
+                      dr, st0 + 2, A.lse));
     float* dWca = G(p + "multihead_attn.in_proj_weight");
     float* dbca = G(p + "multihead_attn.in_proj_bias");
     RC(wgrad(tmp2, C, nullptr, 0, 0, A.n2, C, qpos, Q, dWca, C, dbca, R, C, C, 0.f, qscale, s));                // rows [0, C): Wq

@@ -147,7 +147,8 @@ int self_attn_queries(const float* q, const float* k, const float* v, int ld, fl
 size_t cross_attn_workspace_bytes(int B, int Q, int heads, int S);
 // drop: dropout on the attention probabilities (training), idx = ((b*heads + h)*Q + i)*S + j
 int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
-               void* workspace, cudaStream_t stream, DropCfg drop = drop_off(), uint32_t drop_site = 0);
+               void* workspace, cudaStream_t stream, DropCfg drop = drop_off(), uint32_t drop_site = 0,
+               float* lse_out = nullptr);   // lse_out: optional fp32 [B*heads, Q] row log-sum-exp for cross_attn_bwd
 size_t cross_attn_simt_workspace_bytes(int B, int Q, int heads, int S);
 int cross_attn_simt(const float* q, const bf16* K, const bf16* V, int ldkv, float* out, int B, int Q, int heads, int S,
                     void* workspace, cudaStream_t stream);
@@ -215,7 +216,8 @@ int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const 
 size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S);
 int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
                    bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
-                   DropCfg drop = drop_off(), uint32_t drop_site = 0);
+                   DropCfg drop = drop_off(), uint32_t drop_site = 0,
+                   const float* lse_saved = nullptr);   // the forward's lse_out; recomputed from q, K when absent
 // out[c] = beta*out[c] + sum_r X[r, c]  (X fp32 or bf16, row stride ld); workspace colsum_workspace_bytes(cols)
 size_t colsum_workspace_bytes(long long cols);
 int colsum_rows(const void* X, int is_bf16, long long ld, long long rows, long long cols, float beta, float* out,

@@ -26,6 +26,10 @@ namespace hh {
 namespace {
 
 constexpr int BM = 32, BN = 64, BK = 32, NST = 4;
+#ifndef HH_LIN3_CHAINS
+#define HH_LIN3_CHAINS 1   // accumulator sets the k-steps of a chunk alternate between; measured 1 > 2 > 4: registers (occupancy) matter more than MMA chain length
+#endif
+constexpr int NACC = HH_LIN3_CHAINS;
 constexpr int LDK = BK + 4;     // reduction-contiguous tiles [rows][36]: fragment loads (row g, column t) hit 32 banks
 constexpr int LDA_R = BM + 8;   // reduction-major A tile [32][40]: (row t, column g) -> bank 8 t + g
 constexpr int LDB_R = BN + 8;   // reduction-major B tile [32][72]
@@ -113,28 +117,57 @@ __global__ void __launch_bounds__(256) lin3_kernel(const Lin3Args a) {
   auto a_valid = [&](int red0) {
     return A_KM ? (arow < a.M && red0 + acol < red_end) : (red0 + arow < red_end && acol < a.M);
   };
-  auto b_valid = [&](int it, int red0) {
-    return B_KM ? (brow[it] < a.N && red0 + bcol[it] < red_end) : (red0 + brow[it] < red_end && bcol[it] < a.N);
-  };
+  // Running source pointers of this thread's pieces: chunks are requested strictly in order, so every request is one
+  // compare, one select and one pointer increment (recomputing row * ld + col, and the row modulo of the periodic
+  // addends, per request cost as many instructions as the MMAs of the chunk).
+  const bool a_ok = A_KM ? arow < a.M : acol < a.M;
+  const float* pa = a.A + (A_KM ? static_cast<long long>(arow) * a.lda + red_begin + acol
+                                : static_cast<long long>(red_begin + arow) * a.lda + acol);
+  const long long step_a = A_KM ? BK : static_cast<long long>(BK) * a.lda;
+  const float* pax = a.Ax;
+  long long step_ax = 0;
+  if (has_ax) {
+    if (a.ta == TA_ADD) pax += static_cast<long long>(arow % a.ax_mod) * a.ldax + red_begin + acol;   // forward only (A_KM)
+    else pax += A_KM ? static_cast<long long>(arow) * a.ldax + red_begin + acol
+                     : static_cast<long long>(red_begin + arow) * a.ldax + acol;
+    step_ax = (A_KM || a.ta == TA_ADD) ? BK : static_cast<long long>(BK) * a.ldax;
+  }
+  bool b_ok[2];
+  const float* pb[2];
+  int bxmod[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    b_ok[it] = B_KM ? brow[it] < a.N : bcol[it] < a.N;
+    pb[it] = a.B + (B_KM ? static_cast<long long>(brow[it]) * a.ldb + red_begin + bcol[it]
+                         : static_cast<long long>(red_begin + brow[it]) * a.ldb + bcol[it]);
+    bxmod[it] = has_bx ? (red_begin + brow[it]) % a.bx_mod : 0;   // wgrad only (rows of x run along the reduction)
+  }
+  const long long step_b = B_KM ? BK : static_cast<long long>(BK) * a.ldb;
+  const int bx_step = has_bx ? BK % a.bx_mod : 0;
+  int ld_red0 = red_begin;
   auto load_stage = [&](int c) {
     float* st = smem + (c % NST) * stage_floats;
-    const int red0 = red_begin + c * BK;
     {
-      const bool v = a_valid(red0);
-      const int r = A_KM ? arow : red0 + arow, cc = A_KM ? red0 + acol : acol;
-      cp_async_16(st + a_dst, v ? a.A + static_cast<long long>(r) * a.lda + cc : a.A, v);
+      const bool v = a_ok && ld_red0 + (A_KM ? acol : arow) < red_end;
+      cp_async_16(st + a_dst, v ? pa : a.A, v);
+      pa += step_a;
       if (has_ax) {
-        const int rx = a.ta == TA_ADD ? r % a.ax_mod : r;
-        cp_async_16(st + off_ax + a_dst, v ? a.Ax + static_cast<long long>(rx) * a.ldax + cc : a.Ax, v);
+        cp_async_16(st + off_ax + a_dst, v ? pax : a.Ax, v);
+        pax += step_ax;
       }
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const bool v = b_valid(it, red0);
-      const int r = B_KM ? brow[it] : red0 + brow[it], cc = B_KM ? red0 + bcol[it] : bcol[it];
-      cp_async_16(st + off_b + b_dst[it], v ? a.B + static_cast<long long>(r) * a.ldb + cc : a.B, v);
-      if (has_bx) cp_async_16(st + off_bx + b_dst[it], v ? a.Bx + static_cast<long long>(r % a.bx_mod) * a.ldbx + cc : a.Bx, v);
+      const bool v = b_ok[it] && ld_red0 + (B_KM ? bcol[it] : brow[it]) < red_end;
+      cp_async_16(st + off_b + b_dst[it], v ? pb[it] : a.B, v);
+      pb[it] += step_b;
+      if (has_bx) {
+        cp_async_16(st + off_bx + b_dst[it], v ? a.Bx + static_cast<long long>(bxmod[it]) * a.ldbx + bcol[it] : a.Bx, v);
+        bxmod[it] += bx_step;
+        if (bxmod[it] >= a.bx_mod) bxmod[it] -= a.bx_mod;
+      }
     }
+    ld_red0 += BK;
   };
   // element-wise prologue on this thread's own pieces (its cp.async data is visible to it after wait_group)
   auto transform_stage = [&](int c) {
@@ -192,12 +225,32 @@ __global__ void __launch_bounds__(256) lin3_kernel(const Lin3Args a) {
     const float* Bs = As + off_b;
     // The tensor core truncates when it accumulates: chain only this chunk's 4 k-steps there (the two small correction
     // products in their own accumulator) and add the chunk's partial to the running sum with a rounded fp32 add.
-    float ph[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float pc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    // (even and odd k-steps in separate accumulators: dependent chains of 2 / 4 MMAs instead of 4 / 8)
+    float ph[NACC][2][4], pc[NACC][2][4];
+#pragma unroll
+    for (int i = 0; i < NACC * 8; ++i) (&ph[0][0][0])[i] = (&pc[0][0][0])[i] = 0.f;
+    // Forward (both tiles reduction-contiguous): the MMA's reduction index is a free permutation as long as A and B use
+    // the same one -- thread t takes the chunk's elements 8t .. 8t+7 (k-step ks: 8t + 2ks as k = t, 8t + 2ks + 1 as
+    // k = t + 4), so a fragment row is two 16-byte loads per chunk instead of eight 4-byte ones (rows of 36 floats:
+    // the eight lanes of a quarter-warp phase cover all 32 banks).
+    float av[2][8], bv[2][8];
+    if (MODE == MODE_FWD) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4* ap = reinterpret_cast<const float4*>(As + (wm * 16 + g + h * 8) * LDK + 8 * t);
+        const float4* bp = reinterpret_cast<const float4*>(Bs + (wn * 16 + h * 8 + g) * LDK + 8 * t);
+        *reinterpret_cast<float4*>(&av[h][0]) = ap[0];
+        *reinterpret_cast<float4*>(&av[h][4]) = ap[1];
+        *reinterpret_cast<float4*>(&bv[h][0]) = bp[0];
+        *reinterpret_cast<float4*>(&bv[h][4]) = bp[1];
+      }
+    }
 #pragma unroll
     for (int ks = 0; ks < BK / 8; ++ks) {
       float af[4];
-      if (A_KM) {
+      if (MODE == MODE_FWD) {
+        af[0] = av[0][2 * ks]; af[1] = av[1][2 * ks]; af[2] = av[0][2 * ks + 1]; af[3] = av[1][2 * ks + 1];
+      } else if (A_KM) {
         af[0] = As[(wm * 16 + g) * LDK + ks * 8 + t];     af[1] = As[(wm * 16 + g + 8) * LDK + ks * 8 + t];
         af[2] = As[(wm * 16 + g) * LDK + ks * 8 + t + 4]; af[3] = As[(wm * 16 + g + 8) * LDK + ks * 8 + t + 4];
       } else {
@@ -211,20 +264,25 @@ __global__ void __launch_bounds__(256) lin3_kernel(const Lin3Args a) {
       for (int j = 0; j < 2; ++j) {
         const int n = wn * 16 + j * 8 + g;
         float b0, b1;
-        if (B_KM) { b0 = Bs[n * LDK + ks * 8 + t]; b1 = Bs[n * LDK + ks * 8 + t + 4]; }
+        if (MODE == MODE_FWD) { b0 = bv[j][2 * ks]; b1 = bv[j][2 * ks + 1]; }
         else { b0 = Bs[(ks * 8 + t) * LDB_R + n]; b1 = Bs[(ks * 8 + t + 4) * LDB_R + n]; }
         uint32_t bh0, bl0, bh1, bl1;
         split_fast(b0, bh0, bl0);
         split_fast(b1, bh1, bl1);
-        mma_tf32_1688(pc[j], al, bh0, bh1);
-        mma_tf32_1688(ph[j], ah, bh0, bh1);
-        mma_tf32_1688(pc[j], ah, bl0, bl1);
+        mma_tf32_1688(pc[ks % NACC][j], al, bh0, bh1);
+        mma_tf32_1688(ph[ks % NACC][j], ah, bh0, bh1);
+        mma_tf32_1688(pc[ks % NACC][j], ah, bl0, bl1);
       }
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[j][e] += ph[j][e] + pc[j][e];
+      for (int e = 0; e < 4; ++e) {
+        float hsum = ph[0][j][e], csum = pc[0][j][e];
+#pragma unroll
+        for (int i = 1; i < NACC; ++i) { hsum += ph[i][j][e]; csum += pc[i][j][e]; }
+        acc[j][e] += hsum + csum;
+      }
     if (MODE == MODE_WGRAD && a.db && blockIdx.x == 0 && tid < BM) {
 #pragma unroll 8
       for (int r = 0; r < BK; ++r) bsum += As[r * LDA_R + tid];
