@@ -629,16 +629,19 @@ int self_attn_bwd(const float* q, const float* k, const float* v, int ld, const 
   return 0;
 }
 
-size_t cross_attn_bwd_workspace_bytes(int B, int Q, int heads, int S) {
+size_t cross_attn_bwd_simt_workspace_bytes(int B, int Q, int heads, int S) {
   return static_cast<size_t>(B) * heads * Q * (static_cast<size_t>(S) + 1) * sizeof(float);
 }
 
-int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
-                   bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
-                   DropCfg drop, uint32_t drop_site, const float* lse_saved) {
-  HH_REQUIRE(B > 0 && Q >= 1 && Q <= 16 && heads > 0 && S > 0, "cross_attn_bwd: 1..16 queries");
-  HH_REQUIRE(q && K && V && O && dO && dq && dK && dV && workspace, "cross_attn_bwd: null buffer");
-  HH_REQUIRE(ldkv % 8 == 0 && lddkv % 2 == 0, "cross_attn_bwd: row pitch");
+int cross_lse(const float* q, const bf16* K, int ldkv, float* lse, int B, int Q, int heads, int S, cudaStream_t s) {
+  cross_stats_kernel<<<B * heads, 32 * Q, 0, s>>>(q, K, ldkv, lse, Q, heads, S);
+  HH_CHECK_LAUNCH("cross_stats_kernel");
+  return 0;
+}
+
+int cross_attn_bwd_simt(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
+                        bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
+                        DropCfg drop, uint32_t drop_site, const float* lse_saved) {
   float* lse_ws = static_cast<float*>(workspace);
   float* dS = lse_ws + static_cast<size_t>(B) * heads * Q;
   const float* lse = lse_saved;

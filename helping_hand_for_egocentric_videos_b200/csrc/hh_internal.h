@@ -218,6 +218,13 @@ int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const
                    bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
                    DropCfg drop = drop_off(), uint32_t drop_site = 0,
                    const float* lse_saved = nullptr);   // the forward's lse_out; recomputed from q, K when absent
+// cross_attn_bwd.cu runs the tensor-core kernel; the first-generation SIMT statement (decoder_bwd.cu) serves unaligned
+// operands and HH_CROSS_BWD_SIMT=1
+size_t cross_attn_bwd_simt_workspace_bytes(int B, int Q, int heads, int S);
+int cross_attn_bwd_simt(const float* q, const bf16* K, const bf16* V, int ldkv, const float* O, const float* dO, float* dq,
+                        bf16* dK, bf16* dV, int lddkv, int B, int Q, int heads, int S, void* workspace, cudaStream_t s,
+                        DropCfg drop, uint32_t drop_site, const float* lse_saved);
+int cross_lse(const float* q, const bf16* K, int ldkv, float* lse, int B, int Q, int heads, int S, cudaStream_t s);
 // out[c] = beta*out[c] + sum_r X[r, c]  (X fp32 or bf16, row stride ld); workspace colsum_workspace_bytes(cols)
 size_t colsum_workspace_bytes(long long cols);
 int colsum_rows(const void* X, int is_bf16, long long ld, long long rows, long long cols, float beta, float* out,
