@@ -287,7 +287,7 @@ class TrainShare:
                 + self.R * self.clip.text_flops_per_sequence())
 
     def step(self, video=None, timed_parts=False, wrap=None):
-        """`wrap`: optional {"decoder" | "backward": context-manager factory} put around that part (tools/prof_c4.py)."""
+        """`wrap`: optional {"decoder" | "losses" | "backward": context-manager factory} put around that part (tools/prof_c4.py)."""
         import contextlib
         from helping_hand_for_egocentric_videos_b200 import parallel
         wrap = wrap or {}
@@ -307,18 +307,19 @@ class TrainShare:
             mo, hs, _, _ = self.model(grid)
         if ev:
             ev[2].record()
-        txt = self.model.txt_proj(out["text_feature_map"][self.ar, self.tokens.argmax(-1)])
-        emb = self.model.obj_proj(hs[-1])
-        vid = emb[:, -1].contiguous()
-        verb, noun, pad_rows = self.verb, self.noun, self.pad_rows
-        if self.world > 1:
-            txt, vid, verb, noun, pad_rows = parallel.all_gather_packed([txt, vid, verb, noun, pad_rows])
-        pad = pad_rows[:, None].expand(-1, vid.shape[0]).contiguous()
-        nce, _ = loss.EgoNCE()(metric.sim_matrix(txt, vid), metric.sim_matrix(verb, verb), metric.sim_matrix(noun, noun),
-                               multi_pad_mask=pad, strict_mask=True)
-        lh, _ = box_utils.compute_box_loss('hand_boxes', self.crit, mo, self.px[:, :2].clone(), None, self.sizes, n_queries=12)
-        lo_, _ = box_utils.compute_box_loss('obj_boxes', self.crit, mo, self.px[:, 2:].clone(), None, self.sizes, n_queries=12)
-        word = loss.WordContrastiveLoss()(self.model.txt_proj(self.noun_feats), emb[:, :-1].contiguous(), self.inds)
+        with around("losses"):
+            txt = self.model.txt_proj(out["text_feature_map"][self.ar, self.tokens.argmax(-1)])
+            emb = self.model.obj_proj(hs[-1])
+            vid = emb[:, -1].contiguous()
+            verb, noun, pad_rows = self.verb, self.noun, self.pad_rows
+            if self.world > 1:
+                txt, vid, verb, noun, pad_rows = parallel.all_gather_packed([txt, vid, verb, noun, pad_rows])
+            pad = pad_rows[:, None].expand(-1, vid.shape[0]).contiguous()
+            nce, _ = loss.EgoNCE()(metric.sim_matrix(txt, vid), metric.sim_matrix(verb, verb), metric.sim_matrix(noun, noun),
+                                   multi_pad_mask=pad, strict_mask=True)
+            lh, _ = box_utils.compute_box_loss('hand_boxes', self.crit, mo, self.px[:, :2].clone(), None, self.sizes, n_queries=12)
+            lo_, _ = box_utils.compute_box_loss('obj_boxes', self.crit, mo, self.px[:, 2:].clone(), None, self.sizes, n_queries=12)
+            word = loss.WordContrastiveLoss()(self.model.txt_proj(self.noun_feats), emb[:, :-1].contiguous(), self.inds)
         total = nce + lh + lo_ + 0.5 * word
         if ev:
             ev[3].record()

@@ -362,8 +362,11 @@ int launch_lin3(const Lin3Args& a, int split, cudaStream_t s) {
 
 int linear_f32(const LinArgs& a, cudaStream_t stream) {
   HH_REQUIRE(a.R > 0 && a.N > 0 && a.K > 0, "linear_f32: empty problem");
-  const bool ok = !lin3_disabled() && a.K % 4 == 0 && a.ldi % 4 == 0 && a.N % 2 == 0 && al16(a.in) && al16(a.W) &&
-                  (a.in_add == nullptr || (al16(a.in_add) && a.add_mod > 0));
+  // both generations read the operands in 16-byte pieces
+  HH_REQUIRE(a.K % 4 == 0 && a.ldi % 4 == 0 && al16(a.in) && al16(a.W) && (a.in_add == nullptr || al16(a.in_add)),
+             "linear_f32: input, weight and addend rows must be 16-byte aligned (K and ldi multiples of 4)");
+  HH_REQUIRE(a.in_add == nullptr || a.add_mod > 0, "linear_f32: add_mod");
+  const bool ok = !lin3_disabled() && a.N % 2 == 0;
   if (!ok) return linear_f32_legacy(a, stream);
   Lin3Args l{};
   l.A = a.in; l.lda = a.ldi; l.Ax = a.in_add; l.ldax = a.K; l.ax_mod = a.in_add ? a.add_mod : 1;

@@ -209,6 +209,22 @@ def test_linear_f32(R, N, K):
     _close(ops.linear_f32(x, w, None, in_relu=True), F.linear(F.relu(x), w), 1e-5, 1e-5, "relu+linear")
 
 
+def test_linear_f32_odd_width_and_unaligned_operands():
+    """Shapes lin3.cu refuses (odd N) go to the first-generation kernel; operands that are not 16-byte aligned are an
+    argument error (both kernels read 16-byte pieces), not a misaligned-address fault."""
+    ops = _ops()
+    R, N, K = 70, 33, 64
+    x, w, b = _rand(R, K, seed=43), _rand(N, K, seed=44, scale=1 / math.sqrt(K)), _rand(N, seed=45)
+    _close(ops.linear_f32(x, w, b, act=1), F.relu(F.linear(x, w, b)), 1e-5, 1e-5, "linear (odd N)")
+    flat = _rand(R * K + 1, seed=46)
+    xu = flat[1:].view(R, K)                       # contiguous, 4 bytes off a 16-byte boundary
+    assert xu.data_ptr() % 16 != 0
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        ops.linear_f32(xu, w, b)
+    torch.cuda.synchronize()                      # the context is intact
+    _close(ops.linear_f32(xu.clone(), w, b), F.linear(xu, w, b), 1e-5, 1e-5, "linear (re-aligned copy)")
+
+
 def test_sim_matrix_and_reductions():
     ops = _ops()
     a = _rand(70, 256, seed=50)

@@ -19,7 +19,7 @@ def main():
     torch.cuda.synchronize()
     ts.step(timed_parts=True)
     print("parts (CUDA events):", {k: round(v, 2) for k, v in ts.marks.items()})
-    for part in ("decoder", "backward"):
+    for part in ("decoder", "losses", "backward"):
         prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
 
         class Ctx:
