@@ -114,8 +114,12 @@ struct Decoder {
   DevBuf ws_train, w_kallT, w_vallT;
   DevBuf bw_a, bw_b, bw_c, bw_d, bw_dk, bw_dv, bw_t1, bw_t2, bw_t3, bw_ws;
   std::map<std::string, DevBuf> grads;
+  // second stream of backward() (weight gradients beside the data-gradient chain) and its ordering events
+  cudaStream_t bw_side = nullptr;
+  cudaEvent_t bw_fork = nullptr, bw_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
   explicit Decoder(const hh_decoder_cfg& c);
+  ~Decoder();
   static int validate(const hh_decoder_cfg& c);
   int pack(cudaStream_t s);
   // save = true keeps every layer's activations for backward() (training forward; dropout per next_drop)

@@ -12,6 +12,7 @@
 // The class head has no loss in the reference's criterion (losses = ['boxes', 'cardinality'], run/train.py:471;
 // exclude_class=True), so class_embed receives zero gradients.  Host-side C++ only (kernels: decoder_bwd.cu).
 #include <cmath>
+#include <cstdlib>
 
 #include "engine.h"
 
@@ -87,6 +88,13 @@ int wgrad(const float* dY, int ldy, const float* Y, int ldyo, int act, const flo
 
 }  // namespace
 
+Decoder::~Decoder() {
+  if (bw_side) cudaStreamDestroy(bw_side);
+  if (bw_fork) cudaEventDestroy(bw_fork);
+  for (cudaEvent_t e : bw_done)
+    if (e) cudaEventDestroy(e);
+}
+
 const float* Decoder::grad(const std::string& key) const {
   auto it = grads.find(key);
   return it == grads.end() ? nullptr : static_cast<const float*>(it->second.ptr);
@@ -154,6 +162,41 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
   const bf16* Kall = static_cast<const bf16*>(ws_k.ptr);
   const bf16* Vall = static_cast<const bf16*>(ws_v.ptr);
 
+  // ---- The weight gradients run on a second stream beside the data-gradient chain: at the query side's sizes neither
+  // fills the GPU (208-CTA launches, latency-bound).  fork() orders a weight gradient after everything issued so far;
+  // side_reads(slot) marks the scratch buffer it still reads, before_write(slot) makes the main stream wait for that
+  // reader before a later kernel overwrites the buffer.  HH_BWD_SINGLE_STREAM=1 puts everything back on one stream.
+  static const bool single_stream = [] {
+    const char* e = std::getenv("HH_BWD_SINGLE_STREAM");
+    return e && e[0] == '1';
+  }();
+  enum { SL_DX = 0, SL_GA, SL_GB, SL_TMP2, SL_DQKV, SL_N };
+  if (!single_stream && bw_side == nullptr) {
+    HH_CHECK_CUDA(cudaStreamCreateWithFlags(&bw_side, cudaStreamNonBlocking));
+    HH_CHECK_CUDA(cudaEventCreateWithFlags(&bw_fork, cudaEventDisableTiming));
+    for (int i = 0; i < SL_N; ++i) HH_CHECK_CUDA(cudaEventCreateWithFlags(&bw_done[i], cudaEventDisableTiming));
+  }
+  cudaStream_t sw = single_stream ? s : bw_side;
+  bool pending[SL_N] = {false, false, false, false, false};
+  auto fork = [&]() -> int {
+    if (single_stream) return 0;
+    HH_CHECK_CUDA(cudaEventRecord(bw_fork, s));
+    HH_CHECK_CUDA(cudaStreamWaitEvent(sw, bw_fork, 0));
+    return 0;
+  };
+  auto side_reads = [&](int slot) -> int {
+    if (single_stream) return 0;
+    HH_CHECK_CUDA(cudaEventRecord(bw_done[slot], sw));
+    pending[slot] = true;
+    return 0;
+  };
+  auto before_write = [&](int slot) -> int {
+    if (!pending[slot]) return 0;
+    HH_CHECK_CUDA(cudaStreamWaitEvent(s, bw_done[slot], 0));
+    pending[slot] = false;
+    return 0;
+  };
+
   if (d_hs) HH_CHECK_CUDA(cudaMemcpyAsync(dhs, d_hs, LR * C * 4, cudaMemcpyDeviceToDevice, s));
   else HH_CHECK_CUDA(cudaMemsetAsync(dhs, 0, LR * C * 4, s));
 
@@ -162,20 +205,27 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     const float* box_in = traj ? sv_cond : hs;
     const int RB = static_cast<int>(rows_box);
     // layer 2: boxes = sigmoid(x2 W3^T + b3)
+    RC(fork());
     RC(wgrad(d_boxes, 4, boxes, 4, 2, sv_x2, C, nullptr, 0, G("bbox_embed.layers.2.weight"), C, G("bbox_embed.layers.2.bias"), RB,
-             4, C, 0.f, 1.f, s));
+             4, C, 0.f, 1.f, sw));
     RC(dgrad(d_boxes, 4, boxes, 4, 2, weights.get("bbox_embed.layers.2.weight"), ga, C, RB, 4, C, 0.f, s));
     // layer 1: x2 = relu(x1 W2^T + b2)
+    RC(fork());
     RC(wgrad(ga, C, sv_x2, C, 1, sv_x1, C, nullptr, 0, G("bbox_embed.layers.1.weight"), C, G("bbox_embed.layers.1.bias"), RB, C, C,
-             0.f, 1.f, s));
+             0.f, 1.f, sw));
+    RC(side_reads(SL_GA));
     RC(dgrad(ga, C, sv_x2, C, 1, weights.get("bbox_embed.layers.1.weight"), gb, C, RB, C, C, 0.f, s));
     // layer 0: x1 = relu(box_in W1^T + b1)
+    RC(fork());
     RC(wgrad(gb, C, sv_x1, C, 1, box_in, C, nullptr, 0, G("bbox_embed.layers.0.weight"), C, G("bbox_embed.layers.0.bias"), RB, C, C,
-             0.f, 1.f, s));
+             0.f, 1.f, sw));
+    RC(side_reads(SL_GB));
     if (!traj) {
       RC(dgrad(gb, C, sv_x1, C, 1, weights.get("bbox_embed.layers.0.weight"), dhs, C, RB, C, C, 1.f, s));  // box_in = hs
     } else {
+      RC(before_write(SL_GA));
       RC(dgrad(gb, C, sv_x1, C, 1, weights.get("bbox_embed.layers.0.weight"), ga, C, RB, C, C, 0.f, s));   // ga = d cond
+      RC(before_write(SL_GB));   // dhsproj / dft / dsum live in gb
       // cond[lb,t,q] = hs[lb,q] Wf1^T + (frame_index[t] Wf2^T + bf)      (tfm_decoder.py:212-215)
       float* dhsproj = gb;
       float* dft = gb + LR * C;
@@ -195,10 +245,13 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
       }
       HH_CHECK_LAUNCH("frame_term_bwd_kernel");
       float* dWf = G("frame_proj.weight");  // [C, 2C] = [Wf1 | Wf2]
-      RC(wgrad(dhsproj, C, nullptr, 0, 0, hs, C, nullptr, 0, dWf, 2 * C, nullptr, static_cast<int>(LR), C, C, 0.f, 1.f, s));
+      RC(fork());
+      RC(wgrad(dhsproj, C, nullptr, 0, 0, hs, C, nullptr, 0, dWf, 2 * C, nullptr, static_cast<int>(LR), C, C, 0.f, 1.f, sw));
       RC(dgrad(dhsproj, C, nullptr, 0, 0, static_cast<const float*>(w_f1.ptr), dhs, C, static_cast<int>(LR), C, C, 1.f, s));
+      RC(fork());
       RC(wgrad(dft, C, nullptr, 0, 0, weights.get("frame_index.weight"), C, nullptr, 0, dWf + C, 2 * C, G("frame_proj.bias"), T, C,
-               C, 0.f, 1.f, s));
+               C, 0.f, 1.f, sw));
+      RC(side_reads(SL_GB));
       RC(dgrad(dft, C, nullptr, 0, 0, static_cast<const float*>(w_f2.ptr), G("frame_index.weight"), C, T, C, C, 0.f, s));
     }
   }
@@ -219,48 +272,74 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     const LayerBufs& A = saved[i];
     const float* wsa = static_cast<const float*>(w_sa.ptr) + static_cast<size_t>(i) * 3 * C * C;
     // hs_i = norm(x3): its gradient joins the stream (the norm's weights are shared by all layers: accumulate)
+    RC(before_write(SL_DX));
     RC(ln_bwd(A.x3, "transformer.decoder.norm", dhs + static_cast<size_t>(i) * RC_, i == Lr - 1 ? 0.f : 1.f));
     // ---- FFN: x3 = x2 + drop3(drop(relu(n3 W1^T + b1)) W2^T + b2).  A.f is the hidden AFTER its dropout, so
     // f > 0 <=> (ReLU active and kept) and the inner dropout is only the factor 1/(1-p) on the ReLU derivative
     const uint32_t st0 = static_cast<uint32_t>(i) * 8;
     const float fscale = dr.thr ? dr.scale : 1.f;
-    RC(wgrad(dx, C, nullptr, 0, 0, A.f, Fd, nullptr, 0, G(p + "linear2.weight"), Fd, G(p + "linear2.bias"), R, C, Fd, 0.f, 1.f, s,
+    RC(fork());
+    RC(wgrad(dx, C, nullptr, 0, 0, A.f, Fd, nullptr, 0, G(p + "linear2.weight"), Fd, G(p + "linear2.bias"), R, C, Fd, 0.f, 1.f, sw,
              dr, st0 + 5));
+    RC(side_reads(SL_DX));
+    RC(before_write(SL_GA));
     RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "linear2.weight"), ga, Fd, R, C, Fd, 0.f, s, dr, st0 + 5));  // ga = d f
-    RC(wgrad(ga, Fd, A.f, Fd, 1, A.n3, C, nullptr, 0, G(p + "linear1.weight"), C, G(p + "linear1.bias"), R, Fd, C, 0.f, 1.f, s,
+    RC(fork());
+    RC(wgrad(ga, Fd, A.f, Fd, 1, A.n3, C, nullptr, 0, G(p + "linear1.weight"), C, G(p + "linear1.bias"), R, Fd, C, 0.f, 1.f, sw,
              drop_off(), 0, fscale));
+    RC(side_reads(SL_GA));
     RC(dgrad(ga, Fd, A.f, Fd, 1, weights.get(p + "linear1.weight"), tmp, C, R, Fd, C, 0.f, s, drop_off(), 0, fscale));  // tmp = d n3
+    RC(before_write(SL_DX));
     RC(ln_bwd(A.x2, p + "norm3", tmp, 0.f));
     // ---- cross attention: x2 = x1 + CA(qc, K_i, V_i) Wo^T + bo,  qc = s ((n2 + qpos) Wq^T + bq)
+    RC(fork());
     RC(wgrad(dx, C, nullptr, 0, 0, A.o2, C, nullptr, 0, G(p + "multihead_attn.out_proj.weight"), C,
-             G(p + "multihead_attn.out_proj.bias"), R, C, C, 0.f, 1.f, s, dr, st0 + 3));
+             G(p + "multihead_attn.out_proj.bias"), R, C, C, 0.f, 1.f, sw, dr, st0 + 3));
+    RC(side_reads(SL_DX));
     RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "multihead_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s, dr, st0 + 3));  // tmp = d o2
+    RC(before_write(SL_TMP2));
     RC(cross_attn_bwd(A.qc, Kall + static_cast<size_t>(i) * C, Vall + static_cast<size_t>(i) * C, Lr * C, A.o2, tmp, tmp2,
                       dKall + static_cast<size_t>(i) * C, dVall + static_cast<size_t>(i) * C, Lr * C, B, Q, heads, S, bw_ws.ptr, s,
                       dr, st0 + 2, A.lse));
     float* dWca = G(p + "multihead_attn.in_proj_weight");
     float* dbca = G(p + "multihead_attn.in_proj_bias");
-    RC(wgrad(tmp2, C, nullptr, 0, 0, A.n2, C, qpos, Q, dWca, C, dbca, R, C, C, 0.f, qscale, s));                // rows [0, C): Wq
+    RC(fork());
+    RC(wgrad(tmp2, C, nullptr, 0, 0, A.n2, C, qpos, Q, dWca, C, dbca, R, C, C, 0.f, qscale, sw));                // rows [0, C): Wq
+    RC(side_reads(SL_TMP2));
     RC(dgrad(tmp2, C, nullptr, 0, 0, static_cast<const float*>(w_caq.ptr) + static_cast<size_t>(i) * C * C, tmp, C, R, C, C, 0.f, s));
     RC(colsum_rows(tmp, 0, static_cast<long long>(Q) * C, B, static_cast<long long>(Q) * C, 1.f, G("query_embed.weight"),
                    bw_ws.ptr, s));                                                                               // d qpos
+    RC(before_write(SL_DX));
     RC(ln_bwd(A.x1, p + "norm2", tmp, 0.f));
     // ---- self attention: x1 = x0 + SA(q, k, v) Wo^T + bo;  q, k from n1 + qpos, v from n1
+    RC(fork());
     RC(wgrad(dx, C, nullptr, 0, 0, A.o1, C, nullptr, 0, G(p + "self_attn.out_proj.weight"), C, G(p + "self_attn.out_proj.bias"),
-             R, C, C, 0.f, 1.f, s, dr, st0 + 1));
+             R, C, C, 0.f, 1.f, sw, dr, st0 + 1));
+    RC(side_reads(SL_DX));
     RC(dgrad(dx, C, nullptr, 0, 0, weights.get(p + "self_attn.out_proj.weight"), tmp, C, R, C, C, 0.f, s, dr, st0 + 1));  // tmp = d o1
+    RC(before_write(SL_DQKV));
     RC(self_attn_bwd(A.qkv, A.qkv + C, A.qkv + 2 * C, 3 * C, tmp, dqkv, dqkv + C, dqkv + 2 * C, 3 * C, B, Q, heads, s, dr, st0 + 0));
     float* dWsa = G(p + "self_attn.in_proj_weight");
     float* dbsa = G(p + "self_attn.in_proj_bias");
-    RC(wgrad(dqkv, 3 * C, nullptr, 0, 0, A.n1, C, qpos, Q, dWsa, C, dbsa, R, C, C, 0.f, qscale, s));            // Wq (pre-scaled q)
-    RC(wgrad(dqkv + C, 3 * C, nullptr, 0, 0, A.n1, C, qpos, Q, dWsa + static_cast<size_t>(C) * C, C, dbsa + C, R, C, C, 0.f, 1.f, s));
+    RC(fork());
+    RC(wgrad(dqkv, 3 * C, nullptr, 0, 0, A.n1, C, qpos, Q, dWsa, C, dbsa, R, C, C, 0.f, qscale, sw));            // Wq (pre-scaled q)
+    RC(fork());
+    RC(wgrad(dqkv + C, 3 * C, nullptr, 0, 0, A.n1, C, qpos, Q, dWsa + static_cast<size_t>(C) * C, C, dbsa + C, R, C, C, 0.f, 1.f, sw));
+    RC(fork());
     RC(wgrad(dqkv + 2 * C, 3 * C, nullptr, 0, 0, A.n1, C, nullptr, 0, dWsa + static_cast<size_t>(2) * C * C, C, dbsa + 2 * C, R, C,
-             C, 0.f, 1.f, s));
+             C, 0.f, 1.f, sw));
+    RC(side_reads(SL_DQKV));
     RC(dgrad(dqkv, 3 * C, nullptr, 0, 0, wsa, tmp, C, R, 2 * C, C, 0.f, s));                                     // d(n1 + qpos) via q, k
     RC(colsum_rows(tmp, 0, static_cast<long long>(Q) * C, B, static_cast<long long>(Q) * C, 1.f, G("query_embed.weight"),
                    bw_ws.ptr, s));
     RC(dgrad(dqkv + 2 * C, 3 * C, nullptr, 0, 0, wsa + static_cast<size_t>(2) * C * C, tmp, C, R, C, C, 1.f, s));  // + via v
+    RC(before_write(SL_DX));
     RC(ln_bwd(A.x0, p + "norm1", tmp, 0.f));
+  }
+  // join: the memory side reuses ga / gb, and the caller reads the gradients in stream order
+  if (!single_stream) {
+    HH_CHECK_CUDA(cudaEventRecord(bw_fork, sw));
+    HH_CHECK_CUDA(cudaStreamWaitEvent(s, bw_fork, 0));
   }
   // dx now holds the gradient w.r.t. the zero-initialised tgt: no parameter behind it
 
