@@ -184,14 +184,14 @@ cross_attn_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, c
   }
 }
 
-__global__ void __launch_bounds__(HD)
+__global__ void __launch_bounds__(4 * HD)
 cross_merge_kernel(const float* __restrict__ part, float* __restrict__ out, float* __restrict__ lse, int Q, int heads,
                    int nparts, float oscale) {
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
-  const int d = threadIdx.x;
+  const int d = threadIdx.x & (HD - 1);
   const int C = heads * HD;
   const float* base = part + static_cast<size_t>(blockIdx.x) * nparts * XQ * XPART;
-  for (int i = 0; i < Q; ++i) {
+  for (int i = threadIdx.x / HD; i < Q; i += 4) {   // four query rows per pass
     float mm = -INFINITY;
     for (int s = 0; s < nparts; ++s) mm = fmaxf(mm, base[(s * XQ + i) * XPART]);
     float ll = 0.f, oo = 0.f;
@@ -244,7 +244,7 @@ int cross_attn(const float* q, const bf16* K, const bf16* V, int ldkv, float* ou
   cross_attn_mma_kernel<<<B * heads * splits, XW * 32, smem, stream>>>(q, K, V, ldkv, static_cast<float*>(workspace), Q,
                                                                       heads, S, splits, keys_per_warp, drop, drop_site);
   HH_CHECK_LAUNCH("cross_attn_mma_kernel");
-  cross_merge_kernel<<<B * heads, HD, 0, stream>>>(static_cast<const float*>(workspace), out, lse_out, Q, heads, nparts,
+  cross_merge_kernel<<<B * heads, 4 * HD, 0, stream>>>(static_cast<const float*>(workspace), out, lse_out, Q, heads, nparts,
                                                    drop.thr ? drop.scale : 1.f);
   HH_CHECK_LAUNCH("cross_merge_kernel");
   return 0;

@@ -261,13 +261,13 @@ cross_bwd_mma_kernel(const float* __restrict__ q, const bf16* __restrict__ K, co
   }
 }
 
-__global__ void __launch_bounds__(HD)
+__global__ void __launch_bounds__(4 * HD)
 cross_dq_merge_kernel(const float* __restrict__ part, float* __restrict__ dq, int Q, int heads, int nparts) {
   const int h = blockIdx.x % heads, b = blockIdx.x / heads;
-  const int d = threadIdx.x;
+  const int d = threadIdx.x & (HD - 1);
   const int C = heads * HD;
   const float* base = part + static_cast<size_t>(blockIdx.x) * nparts * XQ * HD;
-  for (int i = 0; i < Q; ++i) {
+  for (int i = threadIdx.x / HD; i < Q; i += 4) {   // four query rows per pass
     float t = 0.f;
     for (int s = 0; s < nparts; ++s) t += base[(s * XQ + i) * HD + d];
     dq[static_cast<size_t>(b * Q + i) * C + h * HD + d] = t;
@@ -324,7 +324,7 @@ int cross_attn_bwd(const float* q, const bf16* K, const bf16* V, int ldkv, const
   cross_bwd_mma_kernel<<<B * heads * splits, XW * 32, smem, s>>>(q, K, V, ldkv, O, dO, lse, dK, dV, lddkv, part, Q, heads, S,
                                                                  splits, keys_per_warp, drop, drop_site);
   HH_CHECK_LAUNCH("cross_bwd_mma_kernel");
-  cross_dq_merge_kernel<<<B * heads, HD, 0, s>>>(part, dq, Q, heads, nparts);
+  cross_dq_merge_kernel<<<B * heads, 4 * HD, 0, s>>>(part, dq, Q, heads, nparts);
   HH_CHECK_LAUNCH("cross_dq_merge_kernel");
   return 0;
 }

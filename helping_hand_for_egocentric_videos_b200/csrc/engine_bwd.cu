@@ -381,13 +381,17 @@ int Decoder::backward(const float* hs, const float* boxes, const float* d_hs, co
     pos3d_bwd_kernel<<<grid, 128, 0, s>>>(dpos, G("pos_embed"), G("temporal_embed"), T, n, C);
     HH_CHECK_LAUNCH("pos3d_bwd_kernel");
   }
-  RC(gemm_bf16(dVall, LC, static_cast<const bf16*>(w_vallT.ptr), LC, dmem, C, nullptr, dmem, C, M, C, LC, EPI_BIAS_RES_F32, s));
+  // d mem = d(mem + pos) + dV_all Wv_all.  The second product goes to its own buffer (gb: the position sums above are consumed)
+  // and pre_norm's backward adds the two: the in-place residual epilogue only exists on the unclustered 1-SM GEMM path
+  // (0.87 ms for this launch against 0.13 ms for its twin above).
+  float* dmem2 = gb;
+  RC(gemm_bf16(dVall, LC, static_cast<const bf16*>(w_vallT.ptr), LC, dmem2, C, nullptr, nullptr, 0, M, C, LC, EPI_BIAS_F32, s));
   // pre_norm backward: memf (fp32, pre-norm) saved by the forward; the bf16 gradient feeds the proj weight GEMM
   bf16* dmemf16 = dKall;  // dK_all is dead: reuse its storage ([BS, C] bf16 fits)
   {
     LnBwdArgs a{};
     a.x = static_cast<const float*>(ws_memf.ptr); a.ldx = C; a.w = weights.get("transformer.pre_norm.weight"); a.eps = 1e-5f;
-    a.dy = dmem; a.lddy = C; a.dx16 = dmemf16;
+    a.dy = dmem; a.dy2 = dmem2; a.lddy = C; a.dx16 = dmemf16;
     a.dgamma = G("transformer.pre_norm.weight"); a.dbeta = G("transformer.pre_norm.bias"); a.beta_w = 0.f;
     a.workspace = bw_ws.ptr; a.M = M; a.D = C;
     RC(ln_backward_rows(a, s));

@@ -202,6 +202,7 @@ struct LnBwdArgs {
   const float* x; int ldx; const bf16* delta;
   const float* w; float eps;
   const float* dy; const bf16* dy16; int lddy;
+  const float* dy2;                 // optional second fp32 addend of dy (same pitch)
   float* dx; bf16* dx16; float beta_dx;
   float* dgamma; float* dbeta; float beta_w;
   void* workspace;  // ln_backward_workspace_bytes(M, D) when dgamma is requested
