@@ -154,6 +154,37 @@ int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t nu
   return 0;
   HH_GUARD_END
 }
+int hh_decoder_get_grads(hh_decoder* dec, const char* const* keys, const int64_t* numels, int n, float* out, int64_t total,
+                         void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec || !keys || !numels || !out || n < 0) return fail(-2, "hh_decoder_get_grads: null argument");
+  int64_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    auto it = dec->impl.weights.expected.find(keys[i]);
+    if (it == dec->impl.weights.expected.end()) return fail(-2, std::string("unknown parameter key '") + keys[i] + "'");
+    if (it->second != numels[i]) return fail(-2, std::string("parameter '") + keys[i] + "': wrong element count");
+    if (off + numels[i] > total) return fail(-2, "hh_decoder_get_grads: output too small");
+    const float* g = dec->impl.grad(keys[i]);
+    if (!g) return fail(-2, "hh_decoder_get_grads: no gradient yet (run hh_decoder_backward)");
+    HH_CHECK_CUDA(cudaMemcpyAsync(out + off, g, static_cast<size_t>(numels[i]) * 4, cudaMemcpyDeviceToDevice, S(stream)));
+    off += numels[i];
+  }
+  if (off != total) return fail(-2, "hh_decoder_get_grads: total does not match the keys");
+  return 0;
+  HH_GUARD_END
+}
+int hh_decoder_set_weights(hh_decoder* dec, const char* const* keys, const float* const* data, const int64_t* numels, int n,
+                           void* stream) {
+  HH_GUARD_BEGIN
+  if (!dec || !keys || !data || !numels || n < 0) return fail(-2, "hh_decoder_set_weights: null argument");
+  for (int i = 0; i < n; ++i) {
+    if (!keys[i] || !data[i]) return fail(-2, "hh_decoder_set_weights: null entry");
+    int rc = dec->impl.weights.set(keys[i], data[i], numels[i], S(stream));
+    if (rc) return rc;
+  }
+  return 0;
+  HH_GUARD_END
+}
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T) { return dec ? dec->impl.flops_per_clip(T) : 0.0; }
 int hh_decoder_last_launches(const hh_decoder* dec) { return dec ? dec->impl.launches : 0; }
 

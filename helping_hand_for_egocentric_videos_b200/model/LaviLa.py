@@ -103,7 +103,9 @@ class _ParamSync:
         self.seen.clear()
         self.checks.clear()
 
-    def sync(self, named, setter):
+    def sync(self, named, setter, batch_setter=None):
+        """`setter(key, tensor)` per changed parameter, or `batch_setter([(key, tensor), ...])` once for all of them."""
+        batch = []
         for key, t in named:
             tag = (t.data_ptr(), t._version, t.dtype)
             if self.seen.get(key) == tag:
@@ -115,10 +117,15 @@ class _ParamSync:
             src = t.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
-            setter(key, src)
+            if batch_setter is not None:
+                batch.append((key, src))
+            else:
+                setter(key, src)
             self.seen[key] = tag
             if self.debug:
                 self.checks[key] = float(t.detach().double().sum().item())
+        if batch:
+            batch_setter(batch)
 
 
 class _DirtyHooks:

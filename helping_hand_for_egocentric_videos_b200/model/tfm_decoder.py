@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
+import math
 import warnings
 
 import torch
@@ -110,15 +111,27 @@ class _DecoderFn(torch.autograd.Function):
         d_hs, d_boxes = prep(d_hs), prep(d_boxes)
         L.check(lib.hh_decoder_backward_checked(m._engine(), ctx.generation, L.ptr(hs), L.ptr(boxes), L.ptr(d_hs),
                                                 L.ptr(d_boxes), L.stream_ptr()), "hh_decoder_backward")
-        grads = []
-        for key, shp, need in zip(ctx.keys, ctx.shapes, ctx.needs_input_grad[2:]):
-            if not need:
-                grads.append(None)
-                continue
-            g = torch.empty(shp, dtype=torch.float32, device=hs.device)
-            L.check(lib.hh_decoder_get_grad(m._engine(), key.encode(), L.ptr(g), g.numel(), L.stream_ptr()),
-                    "hh_decoder_get_grad(%s)" % key)
-            grads.append(g)
+        # one packed read of every requested gradient (135 keys at the c4 step: per-key calls and allocations made this
+        # function host-bound); the returned gradients are views of the one flat tensor
+        needs = tuple(bool(n) for n in ctx.needs_input_grad[2:])
+        want = [(k, shp) for k, shp, need in zip(ctx.keys, ctx.shapes, needs) if need]
+        grads = [None] * len(ctx.keys)
+        if want:
+            cache = getattr(m, "_grad_pack", None)
+            if cache is None or cache[0] != (needs, tuple(ctx.keys), tuple(ctx.shapes)):
+                numels = [int(math.prod(shp)) for _, shp in want]
+                keys_c = (C.c_char_p * len(want))(*[k.encode() for k, _ in want])
+                numels_c = (C.c_int64 * len(want))(*numels)
+                cache = ((needs, tuple(ctx.keys), tuple(ctx.shapes)), keys_c, numels_c, numels, sum(numels))
+                m._grad_pack = cache
+            _, keys_c, numels_c, numels, total = cache
+            flat = torch.empty(total, dtype=torch.float32, device=hs.device)
+            L.check(lib.hh_decoder_get_grads(m._engine(), keys_c, numels_c, len(want), L.ptr(flat), total, L.stream_ptr()),
+                    "hh_decoder_get_grads")
+            pieces = iter(flat.split(numels))
+            for i, (need, shp) in enumerate(zip(needs, ctx.shapes)):
+                if need:
+                    grads[i] = next(pieces).view(shp)
         return (None, None, *grads)
 
 
@@ -265,10 +278,13 @@ class ObjDecoder(_DirtyHooks, nn.Module):
             self._sync = _ParamSync()
         h = self._engine()
 
-        def setter(key, src):
-            L.check(lib.hh_decoder_set_weight(h, key.encode(), L.ptr(src), src.numel(), L.stream_ptr()),
-                    "hh_decoder_set_weight(%s)" % key)
-        self._sync.sync(self._engine_params(), setter)
+        def setter(items):   # every changed parameter in one call (an optimizer step changes all 135)
+            n = len(items)
+            keys_c = (C.c_char_p * n)(*[k.encode() for k, _ in items])
+            ptrs_c = (C.c_void_p * n)(*[L.ptr(t) for _, t in items])
+            numels_c = (C.c_int64 * n)(*[t.numel() for _, t in items])
+            L.check(lib.hh_decoder_set_weights(h, keys_c, ptrs_c, numels_c, n, L.stream_ptr()), "hh_decoder_set_weights")
+        self._sync.sync(self._engine_params(), None, batch_setter=setter)
 
     def flops_per_clip(self, T=None) -> float:
         return L.load().hh_decoder_flops_per_clip(self._engine(), int(T or self.num_frames))

@@ -118,6 +118,13 @@ uint64_t hh_decoder_generation(const hh_decoder* dec);
 int hh_decoder_backward_checked(hh_decoder* dec, uint64_t generation, const float* hs, const float* boxes,
                                 const float* d_hs, const float* d_boxes, void* stream);
 int hh_decoder_get_grad(hh_decoder* dec, const char* key, float* out, int64_t numel, void* stream);
+/* Batched forms (one call per training step instead of one per parameter: the step's 135 keys made the Python side of
+ * the backward host-bound).  get_grads packs the gradients of keys[0..n) back to back into `out` (`total` = sum of
+ * numels); set_weights is hh_decoder_set_weight over n (key, data, numel) triples. */
+int hh_decoder_get_grads(hh_decoder* dec, const char* const* keys, const int64_t* numels, int n, float* out, int64_t total,
+                         void* stream);
+int hh_decoder_set_weights(hh_decoder* dec, const char* const* keys, const float* const* data, const int64_t* numels, int n,
+                           void* stream);
 double hh_decoder_flops_per_clip(const hh_decoder* dec, int T);
 int hh_decoder_last_launches(const hh_decoder* dec);
 
