@@ -858,17 +858,20 @@ def run_train(ctx):
         ms = timed(e2e_step, args.steps)[0] / args.steps
         e2e = {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                "h2d_bytes_per_step": ts.host_video.numel() * 4, "d2h_bytes_per_step": 4}
+    vis, dec = ts.clip.visual, ts.model
+    # the dominant kernel is still the backbone's tcgen05 GEMM; its per-class times come from one profiled step.  EVERY rank
+    # takes this step: at world > 1 it contains the packed all-gather (rank 0 stepping alone would wait for its peers forever)
+    if rank == 0:
+        vis.set_profile(True)
+        vis.profile()
+    ts.step()
+    torch.cuda.synchronize()
     if rank != 0:
         return
-    peaks = load_peaks()
-    flops_clip = ts.flops_per_clip()
-    vis, dec = ts.clip.visual, ts.model
-    # the dominant kernel is still the backbone's tcgen05 GEMM; its per-class times come from one profiled step
-    vis.set_profile(True)
-    vis.profile()
-    ts.step()
     prof = vis.profile()
     vis.set_profile(False)
+    peaks = load_peaks()
+    flops_clip = ts.flops_per_clip()
     M = B * (1 + T * 256)
     gemm_flops = {"gemm_qkv": 2.0 * M * 3072 * 1024, "gemm_proj": 2.0 * M * 1024 * 1024,
                   "gemm_fc1": 2.0 * M * 4096 * 1024, "gemm_fc2": 2.0 * M * 1024 * 4096}
