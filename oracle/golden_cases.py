@@ -47,6 +47,15 @@ CASES = {
     "dec_c2": dict(kind="decoder", seed=25, B=1, G=2,
                    cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=13, n=256, T=16, F=1024, ncls=22047, pred_traj=False),
                    logit_stride=37),
+    # BASELINE c1 decoder geometry (run/test_EgoMCQ.py:236-246): nq = 4 -> Q = 5, 4 frames x 256 patches of 1024-d features,
+    # trajectory head, full class head
+    "dec_c1": dict(kind="decoder", seed=26, B=1, G=2,
+                   cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=5, n=256, T=4, F=1024, ncls=22047, pred_traj=True),
+                   logit_stride=37),
+    # BASELINE c4 decoder geometry (run/train.py:448-458): nq = 12 -> Q = 13 at the same 4 x 256 x 1024 memory, trajectory head
+    "dec_c4": dict(kind="decoder", seed=27, B=2, G=2,
+                   cfg=dict(C=512, heads=8, layers=6, ffn=2048, Q=13, n=256, T=4, F=1024, ncls=22047, pred_traj=True),
+                   logit_stride=37),
     # the decoder in train() mode: dropout at six sites per layer (nn.Dropout x4, both nn.MultiheadAttention modules'
     # attention probabilities) with the masks of hh_oracle.philox_keep injected into the reference through
     # torch.nn.functional.dropout; outputs and the reference's autograd gradients of a fixed linear functional

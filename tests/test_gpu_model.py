@@ -148,7 +148,7 @@ def test_encoder_blocks_against_oracle():
         assert _cos(fmap.cpu(), want) >= 0.9995
 
 
-@pytest.mark.parametrize("name", ["dec_tiny_traj", "dec_tiny_notraj", "dec_c0", "dec_c2"])
+@pytest.mark.parametrize("name", ["dec_tiny_traj", "dec_tiny_notraj", "dec_c0", "dec_c1", "dec_c2", "dec_c4"])
 def test_decoder_against_reference_golden(name):
     case = gc.CASES[name]
     ref = torch.load(os.path.join(gc.GOLDEN_DIR, name + ".pt"))
