@@ -423,7 +423,12 @@ int linear_wgrad_f32(const LinBwdArgs& a, cudaStream_t s) {
   // partial tiles are combined with fp32 atomics (summation order, hence the last bits, vary from run to run).
   const int tiles = ((a.K + BN - 1) / BN) * ((a.N + BM - 1) / BM);
   int split = (4 * num_sms() + tiles - 1) / tiles;
-  const int max_split = (a.R + 127) / 128;   // at least 128 rows (4 chunks: one full ring) per CTA
+  static const int min_rows = [] {   // rows per CTA of the split (HH_LIN3_WGRAD_ROWS: A/B knob)
+    const char* e = std::getenv("HH_LIN3_WGRAD_ROWS");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 32 ? v : 128;
+  }();
+  const int max_split = (a.R + min_rows - 1) / min_rows;   // default: at least 128 rows (4 chunks: one full ring) per CTA
   if (split > max_split) split = max_split;
   if (split > 64) split = 64;
   if (split < 1 || (a.beta != 0.f && a.beta != 1.f)) split = 1;
